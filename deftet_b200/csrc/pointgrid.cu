@@ -1,0 +1,153 @@
+#include "pointgrid.cuh"
+
+namespace dtb {
+
+__device__ __forceinline__ void load_item(const float* items, size_t i, bool tri, float& x, float& y, float& z) {
+    if (!tri) {
+        x = items[i * 3]; y = items[i * 3 + 1]; z = items[i * 3 + 2];
+    } else {
+        const float* f = items + i * 9;
+        x = (f[0] + f[3] + f[6]) * (1.0f / 3.0f);
+        y = (f[1] + f[4] + f[7]) * (1.0f / 3.0f);
+        z = (f[2] + f[5] + f[8]) * (1.0f / 3.0f);
+    }
+}
+
+__global__ void pg_init_kernel(unsigned* bbox_ord, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * 6) bbox_ord[i] = ((i % 6) < 3) ? 0xffffffffu : 0u;
+}
+
+__global__ void __launch_bounds__(256) pg_bbox_kernel(const float* __restrict__ items, bool tri, int N, unsigned* __restrict__ bbox_ord) {
+    int b = blockIdx.y;
+    float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        float x, y, z;
+        load_item(items, (size_t)b * N + i, tri, x, y, z);
+        if (x == x && y == y && z == z) {
+            mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+            mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { mn[k] = warp_min(mn[k]); mx[k] = warp_max(mx[k]); }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (mn[k] <= mx[k]) {
+                atomicMin(&bbox_ord[(size_t)b * 6 + k], f2ord(mn[k]));
+                atomicMax(&bbox_ord[(size_t)b * 6 + 3 + k], f2ord(mx[k]));
+            }
+        }
+    }
+}
+
+// if a sample had no finite item the encoded box is still (max,min): make it a unit box at the origin
+__global__ void pg_fix_bbox_kernel(unsigned* bbox_ord, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    unsigned* q = bbox_ord + (size_t)b * 6;
+    if (q[0] == 0xffffffffu || q[3] == 0u) {
+        for (int k = 0; k < 3; ++k) { q[k] = f2ord(0.0f); q[3 + k] = f2ord(1.0f); }
+    }
+}
+
+__global__ void __launch_bounds__(256) pg_count_kernel(const float* __restrict__ items, bool tri, int N, int G,
+                                                       const unsigned* __restrict__ bbox_ord, unsigned* __restrict__ cell_count,
+                                                       unsigned* __restrict__ cell_of) {
+    int b = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    GridParams g = grid_params(bbox_ord, b, G);
+    float x, y, z;
+    load_item(items, (size_t)b * N + i, tri, x, y, z);
+    int cx = cell_coord(x, g.ox, g.inv_h, G), cy = cell_coord(y, g.oy, g.inv_h, G), cz = cell_coord(z, g.oz, g.inv_h, G);
+    unsigned c = ((unsigned)b * G + cz) * G * G + cy * G + cx;
+    cell_of[(size_t)b * N + i] = c;
+    atomicAdd(&cell_count[c], 1u);
+}
+
+__global__ void __launch_bounds__(256) pg_fill_kernel(const float* __restrict__ items, bool tri, int N,
+                                                      const unsigned* __restrict__ cell_of, unsigned* __restrict__ cell_end,
+                                                      float4* __restrict__ sorted) {
+    int b = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float x, y, z;
+    load_item(items, (size_t)b * N + i, tri, x, y, z);
+    unsigned c = cell_of[(size_t)b * N + i];
+    unsigned dst = atomicAdd(&cell_end[c], 1u);
+    sorted[dst] = make_float4(x, y, z, __int_as_float(i));
+}
+
+__global__ void pg_mask_kernel(const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end, int G, int W,
+                               size_t n_words, unsigned long long* __restrict__ mask) {
+    size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    size_t row = w / W;
+    int x0 = (int)(w % W) * 64;
+    unsigned long long m = 0;
+    for (int k = 0; k < 64 && x0 + k < G; ++k) {
+        size_t c = row * G + x0 + k;
+        if (cell_end[c] > cell_start[c]) m |= (1ull << k);
+    }
+    mask[w] = m;
+}
+
+size_t pointgrid_workspace_bytes(int B, int N, int G, bool with_mask) {
+    Workspace ws(nullptr, 0);
+    PointGrid pg;
+    pointgrid_carve(pg, B, N, G, with_mask, ws);
+    return ws.off;
+}
+
+bool pointgrid_carve(PointGrid& pg, int B, int N, int G, bool with_mask, Workspace& ws) {
+    pg.B = B; pg.N = N; pg.G = G; pg.W = (G + 63) / 64;
+    size_t cells = (size_t)B * G * G * G;
+    pg.bbox_ord = ws.take<unsigned>((size_t)B * 6);
+    pg.cell_start = ws.take<unsigned>(cells);
+    pg.cell_end = ws.take<unsigned>(cells);
+    pg.sorted = ws.take<float4>((size_t)B * N);
+    pg.cell_of = ws.take<unsigned>((size_t)B * N);
+    pg.mask = with_mask ? ws.take<unsigned long long>((size_t)B * G * G * pg.W) : nullptr;
+    pg.scan_ws_bytes = scan_workspace_bytes(cells);
+    pg.scan_ws = ws.take<char>(pg.scan_ws_bytes);
+    return ws.ok;
+}
+
+int pointgrid_build(PointGrid& pg, const float* items, bool tri, cudaStream_t st) {
+    const int B = pg.B, N = pg.N, G = pg.G;
+    size_t cells = (size_t)B * G * G * G;
+    if (cells >= (1ull << 31) || (size_t)B * N >= (1ull << 31)) { set_error("pointgrid: problem too large for 32-bit cell ids"); return DTB_EOVERFLOW; }
+    pg_init_kernel<<<cdiv(B * 6, 128), 128, 0, st>>>(pg.bbox_ord, B);
+    DTB_LAUNCH_CHECK("pg_init");
+    DTB_CUDA(cudaMemsetAsync(pg.cell_start, 0, cells * sizeof(unsigned), st));
+    if (N > 0) {
+        dim3 gb(min(cdiv(N, 256), 64), B);
+        pg_bbox_kernel<<<gb, 256, 0, st>>>(items, tri, N, pg.bbox_ord);
+        DTB_LAUNCH_CHECK("pg_bbox");
+    }
+    pg_fix_bbox_kernel<<<cdiv(B, 128), 128, 0, st>>>(pg.bbox_ord, B);
+    DTB_LAUNCH_CHECK("pg_fix_bbox");
+    if (N > 0) {
+        dim3 gc(cdiv(N, 256), B);
+        pg_count_kernel<<<gc, 256, 0, st>>>(items, tri, N, G, pg.bbox_ord, pg.cell_start, pg.cell_of);
+        DTB_LAUNCH_CHECK("pg_count");
+    }
+    int rc = exclusive_scan_u32(pg.cell_start, pg.cell_start, cells, nullptr, pg.scan_ws, pg.scan_ws_bytes, st);
+    if (rc) return rc;
+    DTB_CUDA(cudaMemcpyAsync(pg.cell_end, pg.cell_start, cells * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+    if (N > 0) {
+        dim3 gc(cdiv(N, 256), B);
+        pg_fill_kernel<<<gc, 256, 0, st>>>(items, tri, N, pg.cell_of, pg.cell_end, pg.sorted);
+        DTB_LAUNCH_CHECK("pg_fill");
+    }
+    if (pg.mask) {
+        size_t n_words = (size_t)B * G * G * pg.W;
+        pg_mask_kernel<<<cdiv((long long)n_words, 256), 256, 0, st>>>(pg.cell_start, pg.cell_end, G, pg.W, n_words, pg.mask);
+        DTB_LAUNCH_CHECK("pg_mask");
+    }
+    return DTB_OK;
+}
+
+}  // namespace dtb

@@ -1,0 +1,377 @@
+// Binned exact-semantics search kernels:
+//   A1  point-in-tet query   (reference layers/DefTet/check_condition_tetrahedron_base/check_condition_tet_for.cu:105-189)
+//       + barycentric weights and their backward (reference has none: utils.py:56-58 returns None; the
+//         weights follow utils/tet_utils.py:28-45 `bary_centric_tet`, the gradient is its autograd)
+//   A2  1-nearest-neighbour  (reference layers/nearest_neighbor/nearest_neighbor_cuda.cu:17-55)
+//
+// The reference scans all T tets / all M points per query thread (O(P*T), O(Q*M)).  Here the query
+// points (A1) or the target points (A2) are counting-sorted into a uniform grid (pointgrid.cu) and
+//   A1: every tet visits only the cells its (slightly inflated) bounding box overlaps and publishes
+//       itself with atomicMin on the point's slot  -> "first containing tet in ascending id" exactly;
+//   A2: every query walks cubic shells of cells outward, pruning with a conservative lower bound, and
+//       keeps the lexicographic minimum of (distance, index) -> "strict <, lowest index wins" exactly.
+// Predicates and distances use the non-contracted fp32 sequence of the reference source (common.cuh x*),
+// so indices are bit-identical to the CPU oracle.
+#include "pointgrid.cuh"
+#include "deftet_b200.h"
+
+namespace dtb {
+
+// ---------------------------------------------------------------------------------------------------
+// A1
+// ---------------------------------------------------------------------------------------------------
+struct FacePlane { float ax, ay, az, nx, ny, nz; bool sv; };
+
+// normal of (b-a)x(c-a), sign of its dot with (d-a): check_condition_tet_for.cu:105-121
+__device__ __forceinline__ FacePlane make_plane(const float* a, const float* b, const float* c, const float* d) {
+    float r1x = xsub(b[0], a[0]), r1y = xsub(b[1], a[1]), r1z = xsub(b[2], a[2]);
+    float r2x = xsub(c[0], a[0]), r2y = xsub(c[1], a[1]), r2z = xsub(c[2], a[2]);
+    FacePlane f;
+    f.ax = a[0]; f.ay = a[1]; f.az = a[2];
+    f.nx = xsub(xmul(r1y, r2z), xmul(r1z, r2y));
+    f.ny = xsub(xmul(r1z, r2x), xmul(r1x, r2z));
+    f.nz = xsub(xmul(r1x, r2y), xmul(r1y, r2x));
+    float dx = xsub(d[0], a[0]), dy = xsub(d[1], a[1]), dz = xsub(d[2], a[2]);
+    float dotv4 = xadd(xadd(xmul(f.nx, dx), xmul(f.ny, dy)), xmul(f.nz, dz));
+    f.sv = dotv4 > 0.f;
+    return f;
+}
+__device__ __forceinline__ bool same_side(const FacePlane& f, float px, float py, float pz) {
+    float dx = xsub(px, f.ax), dy = xsub(py, f.ay), dz = xsub(pz, f.az);
+    float dotp = xadd(xadd(xmul(f.nx, dx), xmul(f.ny, dy)), xmul(f.nz, dz));
+    return (dotp > 0.f) == f.sv;
+}
+
+struct PitIndexed {
+    const float* pos; const int32_t* tet; int V; int T;
+    __device__ __forceinline__ void load(int b, int t, float v[4][3]) const {
+        int4 id = reinterpret_cast<const int4*>(tet)[t];
+        const float* p = pos + (size_t)b * V * 3;
+        int ids[4] = {id.x, id.y, id.z, id.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k][0] = __ldg(p + (size_t)ids[k] * 3); v[k][1] = __ldg(p + (size_t)ids[k] * 3 + 1); v[k][2] = __ldg(p + (size_t)ids[k] * 3 + 2);
+        }
+    }
+};
+struct PitSoup {
+    const float* soup; int T;
+    __device__ __forceinline__ void load(int b, int t, float v[4][3]) const {
+        const float4* q = reinterpret_cast<const float4*>(soup + ((size_t)b * T + t) * 12);
+        float4 x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
+        v[0][0] = x.x; v[0][1] = x.y; v[0][2] = x.z; v[1][0] = x.w; v[1][1] = y.x; v[1][2] = y.y;
+        v[2][0] = y.z; v[2][1] = y.w; v[2][2] = z.x; v[3][0] = z.y; v[3][1] = z.z; v[3][2] = z.w;
+    }
+};
+
+template <typename Src>
+__global__ void __launch_bounds__(128) pit_tet_kernel(Src src, int T, int P, int G, const unsigned* __restrict__ bbox_ord,
+                                                      const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
+                                                      const float4* __restrict__ sorted, int* __restrict__ hit) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    float v[4][3];
+    src.load(b, t, v);
+    float mn[3], mx[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        mn[k] = fminf(fminf(v[0][k], v[1][k]), fminf(v[2][k], v[3][k]));
+        mx[k] = fmaxf(fmaxf(v[0][k], v[1][k]), fmaxf(v[2][k], v[3][k]));
+    }
+    // conservative inflation: the fp32 predicates can accept points a few ulps outside the exact tet
+    float ext = fmaxf(fmaxf(mx[0] - mn[0], mx[1] - mn[1]), mx[2] - mn[2]);
+    float mag = fmaxf(fmaxf(fmaxf(fabsf(mn[0]), fabsf(mx[0])), fmaxf(fabsf(mn[1]), fabsf(mx[1]))), fmaxf(fabsf(mn[2]), fabsf(mx[2])));
+    float margin = 1e-4f * ext + 1e-5f * mag;
+    if (!(margin == margin)) return;                         // NaN vertices never contain anything
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { mn[k] -= margin; mx[k] += margin; }
+    GridParams g = grid_params(bbox_ord, b, G);
+    float gmax = g.h * (float)G;
+    if (mx[0] < g.ox || mx[1] < g.oy || mx[2] < g.oz || mn[0] > g.ox + gmax * 1.0001f || mn[1] > g.oy + gmax * 1.0001f ||
+        mn[2] > g.oz + gmax * 1.0001f)
+        return;
+    int x0 = cell_coord(mn[0], g.ox, g.inv_h, G), x1 = cell_coord(mx[0], g.ox, g.inv_h, G);
+    int y0 = cell_coord(mn[1], g.oy, g.inv_h, G), y1 = cell_coord(mx[1], g.oy, g.inv_h, G);
+    int z0 = cell_coord(mn[2], g.oz, g.inv_h, G), z1 = cell_coord(mx[2], g.oz, g.inv_h, G);
+    // the four rotations (a,b,c,d),(b,a,d,c),(c,d,a,b),(d,c,b,a) of check_condition_tet_for.cu:172-175
+    FacePlane f1 = make_plane(v[0], v[1], v[2], v[3]);
+    FacePlane f2 = make_plane(v[1], v[0], v[3], v[2]);
+    FacePlane f3 = make_plane(v[2], v[3], v[0], v[1]);
+    FacePlane f4 = make_plane(v[3], v[2], v[1], v[0]);
+    int* hb = hit + (size_t)b * P;
+    const size_t cbase = (size_t)b * G * G * G;
+    for (int z = z0; z <= z1; ++z)
+        for (int y = y0; y <= y1; ++y) {
+            size_t row = cbase + ((size_t)z * G + y) * G;
+            unsigned j0 = cell_start[row + x0], j1 = cell_end[row + x1];
+            for (unsigned j = j0; j < j1; ++j) {
+                float4 q = __ldg(sorted + j);
+                if (q.x < mn[0] || q.x > mx[0] || q.y < mn[1] || q.y > mx[1] || q.z < mn[2] || q.z > mx[2]) continue;
+                bool s1 = same_side(f1, q.x, q.y, q.z), s2 = same_side(f2, q.x, q.y, q.z);
+                bool s3 = same_side(f3, q.x, q.y, q.z), s4 = same_side(f4, q.x, q.y, q.z);
+                if (s1 == s2 && s2 == s3 && s3 == s4) atomicMin(hb + __float_as_int(q.w), t);
+            }
+        }
+}
+
+// bary_centric_tet (utils/tet_utils.py:28-45): ratios of scalar triple products
+__device__ __forceinline__ float triple(const float* a, const float* b, const float* c) {
+    return a[0] * (b[1] * c[2] - b[2] * c[1]) + a[1] * (b[2] * c[0] - b[0] * c[2]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
+}
+__device__ __forceinline__ void bary_weights(const float v[4][3], const float* p, float* w) {
+    float vap[3], vbp[3], vab[3], vac[3], vad[3], vbc[3], vbd[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        vap[k] = p[k] - v[0][k]; vbp[k] = p[k] - v[1][k];
+        vab[k] = v[1][k] - v[0][k]; vac[k] = v[2][k] - v[0][k]; vad[k] = v[3][k] - v[0][k];
+        vbc[k] = v[2][k] - v[1][k]; vbd[k] = v[3][k] - v[1][k];
+    }
+    float v6 = 1.0f / triple(vab, vac, vad);
+    w[0] = triple(vbp, vbd, vbc) * v6;
+    w[1] = triple(vap, vac, vad) * v6;
+    w[2] = triple(vap, vad, vab) * v6;
+    w[3] = triple(vap, vab, vac) * v6;
+}
+
+template <typename Src>
+__global__ void __launch_bounds__(256) pit_finalize_kernel(Src src, const float* __restrict__ points, int P, const int* __restrict__ hit,
+                                                           float* __restrict__ cond, float* __restrict__ bary) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    int t = hit[(size_t)b * P + i];
+    bool found = t != 0x7f7f7f7f;
+    if (cond) cond[(size_t)b * P + i] = found ? (float)t : -1.0f;
+    if (bary) {
+        float w[4] = {0.f, 0.f, 0.f, 0.f};
+        if (found) {
+            float v[4][3];
+            src.load(b, t, v);
+            const float* p = points + ((size_t)b * P + i) * 3;
+            float pp[3] = {p[0], p[1], p[2]};
+            bary_weights(v, pp, w);
+        }
+        reinterpret_cast<float4*>(bary)[(size_t)b * P + i] = make_float4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// backward of the barycentric weights: with E = [b-a, c-a, d-a] (columns), lambda = E^-1 (p - a),
+// h = E^-T (g_b-g_a, g_c-g_a, g_d-g_a):  dL/dp = h,  dL/dv_i = -w_i h  (i = a,b,c,d).
+__global__ void __launch_bounds__(256) bary_backward_kernel(const float* __restrict__ pos, const int32_t* __restrict__ tet, int V,
+                                                            const float* __restrict__ points, int P, const float* __restrict__ cond,
+                                                            const float* __restrict__ g_w, float* __restrict__ grad_pos,
+                                                            float* __restrict__ grad_points) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    size_t o = (size_t)b * P + i;
+    float c = cond[o];
+    float h[3] = {0.f, 0.f, 0.f};
+    if (c >= 0.f) {
+        int t = (int)c;
+        int4 id = reinterpret_cast<const int4*>(tet)[t];
+        const float* pb = pos + (size_t)b * V * 3;
+        int ids[4] = {id.x, id.y, id.z, id.w};
+        float v[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[k][0] = pb[(size_t)ids[k] * 3]; v[k][1] = pb[(size_t)ids[k] * 3 + 1]; v[k][2] = pb[(size_t)ids[k] * 3 + 2]; }
+        float p[3] = {points[o * 3], points[o * 3 + 1], points[o * 3 + 2]};
+        float w[4];
+        bary_weights(v, p, w);
+        float4 g = reinterpret_cast<const float4*>(g_w)[o];
+        float gb = g.y - g.x, gc = g.z - g.x, gd = g.w - g.x;
+        // rows of E^-1 are (c-a)x(d-a), (d-a)x(b-a), (b-a)x(c-a) over det; h = sum_i gbar_i * row_i
+        float e1[3], e2[3], e3[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { e1[k] = v[1][k] - v[0][k]; e2[k] = v[2][k] - v[0][k]; e3[k] = v[3][k] - v[0][k]; }
+        float r1[3] = {e2[1] * e3[2] - e2[2] * e3[1], e2[2] * e3[0] - e2[0] * e3[2], e2[0] * e3[1] - e2[1] * e3[0]};
+        float r2[3] = {e3[1] * e1[2] - e3[2] * e1[1], e3[2] * e1[0] - e3[0] * e1[2], e3[0] * e1[1] - e3[1] * e1[0]};
+        float r3[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+        float inv = 1.0f / (e1[0] * r1[0] + e1[1] * r1[1] + e1[2] * r1[2]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) h[k] = (gb * r1[k] + gc * r2[k] + gd * r3[k]) * inv;
+        if (grad_pos) {
+            float* gp = grad_pos + (size_t)b * V * 3;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) atomicAdd(gp + (size_t)ids[q] * 3 + k, -w[q] * h[k]);
+        }
+    }
+    if (grad_points) { grad_points[o * 3] = h[0]; grad_points[o * 3 + 1] = h[1]; grad_points[o * 3 + 2] = h[2]; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A2
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) nn_query_kernel(const float* __restrict__ queries, int Q, int G, int W,
+                                                       const unsigned* __restrict__ bbox_ord, const unsigned* __restrict__ cell_start,
+                                                       const unsigned* __restrict__ cell_end, const float4* __restrict__ sorted,
+                                                       const unsigned long long* __restrict__ mask, int* __restrict__ result) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q) return;
+    const float* qp = queries + ((size_t)b * Q + i) * 3;
+    const float qx = qp[0], qy = qp[1], qz = qp[2];
+    GridParams g = grid_params(bbox_ord, b, G);
+    const int cx = cell_coord(qx, g.ox, g.inv_h, G), cy = cell_coord(qy, g.oy, g.inv_h, G), cz = cell_coord(qz, g.oz, g.inv_h, G);
+    float best = 1e20f;      // nearest_neighbor_cuda.cu:28-29
+    int bi = 0;
+    const size_t cbase = (size_t)b * G * G * G;
+    const size_t mbase = (size_t)b * G * G * W;
+    for (int r = 0; r < G; ++r) {
+        if (r >= 1) {
+            float lb = (float)(r - 1) * g.h * 0.999f;      // every point of shell r is at least this far (conservative)
+            if (lb * lb > best) break;
+        }
+        int z0 = max(cz - r, 0), z1 = min(cz + r, G - 1), y0 = max(cy - r, 0), y1 = min(cy + r, G - 1);
+        int xa = cx - r, xb = cx + r;
+        for (int z = z0; z <= z1; ++z) {
+            bool zface = (z == cz - r) || (z == cz + r);
+            for (int y = y0; y <= y1; ++y) {
+                bool full = zface || (y == cy - r) || (y == cy + r);
+                const unsigned long long* mrow = mask + mbase + ((size_t)z * G + y) * W;
+                size_t row = cbase + ((size_t)z * G + y) * G;
+                for (int w = 0; w < W; ++w) {
+                    int lo = w * 64;
+                    unsigned long long sel;
+                    if (full) {
+                        int a = max(xa, lo), e = min(xb, lo + 63);
+                        if (a > e) continue;
+                        int n = e - a + 1;
+                        sel = (n >= 64 ? ~0ull : ((1ull << n) - 1ull)) << (a - lo);
+                    } else {
+                        sel = 0ull;
+                        if (xa >= lo && xa < lo + 64) sel |= 1ull << (xa - lo);
+                        if (xb >= lo && xb < lo + 64 && xb < G) sel |= 1ull << (xb - lo);
+                        if (!sel) continue;
+                    }
+                    unsigned long long m = __ldg(mrow + w) & sel;
+                    while (m) {
+                        int k = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        size_t c = row + lo + k;
+                        unsigned j0 = cell_start[c], j1 = cell_end[c];
+                        for (unsigned j = j0; j < j1; ++j) {
+                            float4 p = __ldg(sorted + j);
+                            float dx = xsub(p.x, qx), dy = xsub(p.y, qy), dz = xsub(p.z, qz);
+                            float d = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
+                            int idx = __float_as_int(p.w);
+                            if (d < best || (d == best && idx < bi)) { best = d; bi = idx; }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    result[(size_t)b * Q + i] = bi;
+}
+
+}  // namespace dtb
+
+using namespace dtb;
+
+static int default_grid_res(long long n_items, int lo, int hi) {
+    int g = (int)ceil(cbrt((double)(n_items > 1 ? n_items : 1)));
+    if (g < lo) g = lo;
+    if (g > hi) g = hi;
+    return g;
+}
+
+// ---- A1 -------------------------------------------------------------------------------------------
+extern "C" int dtb_point_in_tet_grid_res(int T, int P) {
+    (void)P;
+    return default_grid_res(T, 4, 160);
+}
+extern "C" size_t dtb_point_in_tet_workspace(int B, int P, int T, int G) {
+    if (G <= 0) G = dtb_point_in_tet_grid_res(T, P);
+    return pointgrid_workspace_bytes(B, P, G, false) + align_up((size_t)B * P * sizeof(int), 256);
+}
+
+template <typename Src>
+static int point_in_tet_impl(Src src, const float* points, int B, int T, int P, int G, float* cond, float* bary, void* workspace,
+                             size_t workspace_bytes, cudaStream_t st) {
+    DTB_REQUIRE(B > 0 && P >= 0 && T >= 0 && T < 0x7f7f7f7f, "point_in_tet: bad sizes B=%d P=%d T=%d", B, P, T);
+    if (P == 0) return DTB_OK;
+    if (G <= 0) G = dtb_point_in_tet_grid_res(T, P);
+    Workspace ws(workspace, workspace_bytes);
+    PointGrid pg;
+    pointgrid_carve(pg, B, P, G, false, ws);
+    int* hit = ws.take<int>((size_t)B * P);
+    if (!ws.ok || !workspace) { set_error("point_in_tet: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return DTB_EWORKSPACE; }
+    int rc = pointgrid_build(pg, points, false, st);
+    if (rc) return rc;
+    DTB_CUDA(cudaMemsetAsync(hit, 0x7f, (size_t)B * P * sizeof(int), st));    // 0x7f7f7f7f: larger than any tet id
+    if (T > 0) {
+        dim3 grid(cdiv(T, 128), B);
+        pit_tet_kernel<Src><<<grid, 128, 0, st>>>(src, T, P, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, hit);
+        DTB_LAUNCH_CHECK("pit_tet");
+    }
+    dim3 gf(cdiv(P, 256), B);
+    pit_finalize_kernel<Src><<<gf, 256, 0, st>>>(src, points, P, hit, cond, bary);
+    DTB_LAUNCH_CHECK("pit_finalize");
+    return DTB_OK;
+}
+
+extern "C" int dtb_point_in_tet(const float* pos, const int32_t* tet, const float* points, int B, int V, int T, int P, int G,
+                                float* cond, float* bary, void* workspace, size_t workspace_bytes, void* stream) {
+    DTB_REQUIRE(pos && tet && points, "point_in_tet: null argument");
+    PitIndexed src{pos, tet, V, T};
+    return point_in_tet_impl(src, points, B, T, P, G, cond, bary, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dtb_point_in_tet_soup(const float* tet_bxfx4x3, const float* points, int B, int T, int P, int G, float* cond,
+                                     float* bary, void* workspace, size_t workspace_bytes, void* stream) {
+    DTB_REQUIRE(tet_bxfx4x3 && points, "point_in_tet_soup: null argument");
+    PitSoup src{tet_bxfx4x3, T};
+    return point_in_tet_impl(src, points, B, T, P, G, cond, bary, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dtb_tet_barycentric_backward(const float* pos, const int32_t* tet, const float* points, const float* cond,
+                                            const float* g_w, int B, int V, int T, int P, float* grad_pos, float* grad_points,
+                                            void* stream) {
+    (void)T;
+    DTB_REQUIRE(pos && tet && points && cond && g_w, "tet_barycentric_backward: null argument");
+    if (P == 0 || B == 0) return DTB_OK;
+    dim3 grid(cdiv(P, 256), B);
+    bary_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pos, tet, V, points, P, cond, g_w, grad_pos, grad_points);
+    DTB_LAUNCH_CHECK("bary_backward");
+    return DTB_OK;
+}
+
+// ---- A2 -------------------------------------------------------------------------------------------
+extern "C" int dtb_nearest_neighbor_grid_res(int M) {
+    // target points usually sample a surface: ~M^(1/2) cells per axis keeps a few points per occupied cell
+    int g = (int)ceil(sqrt((double)(M > 1 ? M : 1)) * 0.35);
+    if (g < 4) g = 4;
+    if (g > 128) g = 128;
+    return g;
+}
+extern "C" size_t dtb_nearest_neighbor_workspace(int B, int Q, int M, int G) {
+    (void)Q;
+    if (G <= 0) G = dtb_nearest_neighbor_grid_res(M);
+    return pointgrid_workspace_bytes(B, M, G, true);
+}
+extern "C" int dtb_nearest_neighbor(const float* queries, const float* points, int32_t* result, int B, int Q, int M, int G,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    DTB_REQUIRE(B > 0 && Q >= 0 && M >= 0, "nearest_neighbor: bad sizes");
+    if (Q == 0) return DTB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DTB_REQUIRE(queries && points && result, "nearest_neighbor: null argument");
+    if (M == 0) {                       // reference leaves the zero-initialised result untouched
+        DTB_CUDA(cudaMemsetAsync(result, 0, (size_t)B * Q * sizeof(int), st));
+        return DTB_OK;
+    }
+    if (G <= 0) G = dtb_nearest_neighbor_grid_res(M);
+    Workspace ws(workspace, workspace_bytes);
+    PointGrid pg;
+    pointgrid_carve(pg, B, M, G, true, ws);
+    if (!ws.ok || !workspace) { set_error("nearest_neighbor: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return DTB_EWORKSPACE; }
+    int rc = pointgrid_build(pg, points, false, st);
+    if (rc) return rc;
+    dim3 grid(cdiv(Q, 128), B);
+    nn_query_kernel<<<grid, 128, 0, st>>>(queries, Q, G, pg.W, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask, result);
+    DTB_LAUNCH_CHECK("nn_query");
+    return DTB_OK;
+}

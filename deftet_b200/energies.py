@@ -1,0 +1,123 @@
+"""Per-tet energies as autograd Functions over the fused sm_100a kernels (csrc/energies.cu).
+
+Host-side mirror of ``DefTet.amips_energy / volume_variance / edge_length / tet_inverse_v``
+(reference ``layers/DefTet/deftet.py:239-338``).  Two call forms:
+
+* ``tet_energies(pos, tet, inv_v)`` -- the engine form: vertex positions (B,V,3) + shared int32 topology
+  (T,4); never materialises the (B,T,4,3) gather, gradient is scattered straight into (B,V,3).
+* ``amips_energy_soup / volume_variance_soup / edge_length_soup(tet_bxfx4x3, ...)`` -- the drop-in form
+  with exactly the tensors the reference methods receive.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+AMIPS, EDGE, VOLUME, ALL = 1, 2, 4, 7
+
+
+def _f32c(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+def tet_inverse_v(init_pos: torch.Tensor, tet: torch.Tensor) -> torch.Tensor:
+    """(T,3,3) inverse of the 20x-scaled rest offset matrix; singular -> identity (deftet.py:205-233,300-318)."""
+    _lib.require_cuda(init_pos, tet)
+    pos = _f32c(init_pos)
+    tet32 = tet.to(torch.int32).contiguous()
+    T = tet32.shape[0]
+    out = torch.empty(T, 3, 3, device=pos.device, dtype=torch.float32)
+    with torch.cuda.device(pos.device):
+        _lib.check(_lib.lib().dtb_tet_inverse_v(_lib.ptr(pos), _lib.ptr(tet32), pos.shape[0], T, _lib.ptr(out),
+                                               _lib.stream_ptr()), "dtb_tet_inverse_v")
+    return out
+
+
+class _TetEnergies(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, tet32, inv_v, flags):
+        _lib.require_cuda(pos, tet32)
+        pos = _f32c(pos)
+        B, V, _ = pos.shape
+        T = tet32.shape[0]
+        dev = pos.device
+        L = _lib.lib()
+        out = torch.zeros(3, B, device=dev, dtype=torch.float32)
+        stats = torch.empty(B, 8, device=dev, dtype=torch.float64)
+        wsz = L.dtb_tet_energies_workspace(B, V, T)
+        ws = torch.empty(wsz, device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            _lib.check(L.dtb_tet_energies_forward(_lib.ptr(pos), _lib.ptr(tet32), _lib.ptr(inv_v), B, V, T, flags,
+                                                  _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(stats),
+                                                  _lib.ptr(ws), wsz, _lib.stream_ptr()), "dtb_tet_energies_forward")
+        ctx.save_for_backward(pos, tet32, inv_v, stats)
+        ctx.flags = flags
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_amips, g_edge, g_vol):
+        pos, tet32, inv_v, stats = ctx.saved_tensors
+        B, V, _ = pos.shape
+        T = tet32.shape[0]
+        grad = torch.zeros_like(pos)
+        gs = [None if g is None else _f32c(g) for g in (g_amips, g_edge, g_vol)]
+        with torch.cuda.device(pos.device):
+            _lib.check(_lib.lib().dtb_tet_energies_backward(_lib.ptr(pos), _lib.ptr(tet32), _lib.ptr(inv_v), B, V, T,
+                                                            ctx.flags, _lib.ptr(stats), _lib.ptr(gs[0]), _lib.ptr(gs[1]),
+                                                            _lib.ptr(gs[2]), _lib.ptr(grad), _lib.stream_ptr()),
+                       "dtb_tet_energies_backward")
+        return grad, None, None, None
+
+
+def tet_energies(pos, tet32, inv_v, flags=ALL):
+    """-> (amips (B,), edge (B,), volume_variance (B,)) for vertex positions (B,V,3)."""
+    if tet32.dtype != torch.int32:
+        tet32 = tet32.to(torch.int32)
+    return _TetEnergies.apply(pos, tet32.contiguous(), None if inv_v is None else _f32c(inv_v), int(flags))
+
+
+class _SoupEnergies(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, soup, inv_v, flags):
+        _lib.require_cuda(soup)
+        soup = _f32c(soup)
+        B, T = soup.shape[0], soup.shape[1]
+        dev = soup.device
+        L = _lib.lib()
+        out = torch.zeros(3, B, device=dev, dtype=torch.float32)
+        stats = torch.empty(B, 8, device=dev, dtype=torch.float64)
+        wsz = L.dtb_tet_energies_workspace(B, 0, T)
+        ws = torch.empty(wsz, device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            _lib.check(L.dtb_tet_energies_forward_soup(_lib.ptr(soup), _lib.ptr(inv_v), B, T, flags, _lib.ptr(out[0]),
+                                                       _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(stats), _lib.ptr(ws),
+                                                       wsz, _lib.stream_ptr()), "dtb_tet_energies_forward_soup")
+        ctx.save_for_backward(soup, inv_v, stats)
+        ctx.flags = flags
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_amips, g_edge, g_vol):
+        soup, inv_v, stats = ctx.saved_tensors
+        B, T = soup.shape[0], soup.shape[1]
+        grad = torch.empty_like(soup)
+        gs = [None if g is None else _f32c(g) for g in (g_amips, g_edge, g_vol)]
+        with torch.cuda.device(soup.device):
+            _lib.check(_lib.lib().dtb_tet_energies_backward_soup(_lib.ptr(soup), _lib.ptr(inv_v), B, T, ctx.flags,
+                                                                 _lib.ptr(stats), _lib.ptr(gs[0]), _lib.ptr(gs[1]),
+                                                                 _lib.ptr(gs[2]), _lib.ptr(grad), _lib.stream_ptr()),
+                       "dtb_tet_energies_backward_soup")
+        return grad, None, None
+
+
+def amips_energy_soup(tet_bxfx4x3, inverse_v):
+    return _SoupEnergies.apply(tet_bxfx4x3, _f32c(inverse_v), AMIPS)[0]
+
+
+def edge_length_soup(tet_bxfx4x3):
+    return _SoupEnergies.apply(tet_bxfx4x3, None, EDGE)[1]
+
+
+def volume_variance_soup(tet_bxfx4x3):
+    return _SoupEnergies.apply(tet_bxfx4x3, None, VOLUME)[2]

@@ -1,0 +1,109 @@
+/* deftet_b200 -- C ABI of the Blackwell-native differentiable-tetrahedra engine.
+ *
+ * One shared library (deftet_b200/libdeftet_b200.so, sm_100a only, no CPU fallback) exports everything the
+ * reference's per-tetrahedron hot path binds through pybind11 / ctypes.  Plain
+ * pointers and sizes only; no torch types.  Two families of entry points:
+ *
+ *   dtb_*            device-pointer API: all array arguments are DEVICE pointers, work is enqueued on
+ *                    `stream` (a cudaStream_t passed as void*) of the CURRENT device, nothing synchronises
+ *                    unless stated.  Temporary memory comes from a caller-provided workspace whose size the
+ *                    matching *_workspace() function reports (so the hot path never calls cudaMalloc).
+ *   dtb_host_*       host-pointer API with exactly the argument lists of the reference's ctypes
+ *                    `extern "C" void run(...)` builders (utils/lib/<name>/run.cpp) -- blocking, copies
+ *                    in/out itself.
+ *
+ * Return value: 0 on success, <0 DTB_E* or >0 cudaError_t; dtb_last_error() gives the message (thread
+ * local).  All functions are re-entrant and keep no global mutable state besides that message, which is
+ * what nn.DataParallel's one-thread-per-GPU calling pattern needs (train_multigpu.py:136-140).
+ *
+ * Each declaration cites the reference interface it replaces (file:line relative to the reference root).
+ */
+#ifndef DEFTET_B200_H
+#define DEFTET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTB_ENERGY_AMIPS 1
+#define DTB_ENERGY_EDGE 2
+#define DTB_ENERGY_VOLUME 4
+#define DTB_ENERGY_ALL 7
+
+/* ---- library ------------------------------------------------------------------------------------ */
+const char* dtb_last_error(void);
+int dtb_version(void);                 /* 100 * major + minor */
+int dtb_device_is_sm100(int device);   /* 1 if the device is compute capability 10.x, 0 if not, <0 on error */
+
+/* ---- A6/A7/A8: per-tet energies -------------------------------------------------------------------
+ * Replaces DefTet.amips_energy / volume_variance / edge_length + autograd
+ * (layers/DefTet/deftet.py:266-298, 239-263, 320-338) and tet_inverse_v/my_inverse (:205-233, 300-318).
+ * pos (B,V,3) f32, tet (T,4) i32 (shared by the batch), inv_v (T,3,3) f32; outputs (B,) f32 each.
+ * stats: (B,8) f64 scratch that forward fills and backward reads (sums, centred moments, mean volume).
+ * flags: DTB_ENERGY_* mask; outputs of unselected energies are untouched and may be NULL.
+ * backward ACCUMULATES into grad_pos (B,V,3) (caller zero-fills); g_* are the upstream (B,) gradients, a
+ * NULL g_* means "no gradient requested for that energy".
+ * The *_soup variants take the materialised tet_bxfx4x3 (B,T,4,3) tensor the reference methods receive
+ * (deftet.py:66-68) and write a dense (B,T,4,3) gradient (overwritten, not accumulated). */
+size_t dtb_tet_energies_workspace(int B, int V, int T);
+int dtb_tet_energies_forward(const float* pos, const int32_t* tet, const float* inv_v, int B, int V, int T, int flags,
+                             float* amips, float* edge, float* volvar, double* stats, void* workspace,
+                             size_t workspace_bytes, void* stream);
+int dtb_tet_energies_backward(const float* pos, const int32_t* tet, const float* inv_v, int B, int V, int T, int flags,
+                              const double* stats, const float* g_amips, const float* g_edge, const float* g_volvar,
+                              float* grad_pos, void* stream);
+int dtb_tet_energies_forward_soup(const float* tet_bxfx4x3, const float* inv_v, int B, int T, int flags, float* amips,
+                                  float* edge, float* volvar, double* stats, void* workspace, size_t workspace_bytes,
+                                  void* stream);
+int dtb_tet_energies_backward_soup(const float* tet_bxfx4x3, const float* inv_v, int B, int T, int flags,
+                                   const double* stats, const float* g_amips, const float* g_edge,
+                                   const float* g_volvar, float* grad_soup, void* stream);
+int dtb_tet_inverse_v(const float* pos0, const int32_t* tet, int V, int T, float* inv_v, void* stream);
+
+/* ---- A1: point-in-tet occupancy query + barycentric weights ------------------------------------------
+ * Replaces check_condition_cuda_tet_base.forward(tet_bxfx4x3, point_pos_bxnx3, condition_bxnx1, bbox_filter_bxfx6)
+ * (layers/DefTet/check_condition_tetrahedron_base/check_condition_tet.cpp:31-48, kernel
+ * check_condition_tet_for.cu:124-189): cond (B,P) f32 = index of the FIRST tet (ascending id) whose four
+ * same-side predicates agree, else -1.  bbox_filter_bxfx6 of the reference is dead (kernel lines :154-164
+ * are commented out) and has no counterpart.  bary (B,P,4) f32, optional: weights of
+ * utils/tet_utils.py:28-45 `bary_centric_tet` w.r.t. the found tet (zeros where cond == -1).
+ * G: cells per axis of the uniform grid the points are binned into, <= 0 selects dtb_point_in_tet_grid_res.
+ * _soup takes the materialised (B,T,4,3) tensor exactly as the reference does; the indexed form takes
+ * pos (B,V,3) + tet (T,4) i32 and never materialises it.
+ * dtb_tet_barycentric_backward: the reference defines no backward (utils.py:56-58 returns None, None); this
+ * is autograd of bary_centric_tet: g_w (B,P,4) -> ACCUMULATES into grad_pos (B,V,3) (may be NULL) and
+ * overwrites grad_points (B,P,3) (may be NULL). */
+int dtb_point_in_tet_grid_res(int T, int P);
+size_t dtb_point_in_tet_workspace(int B, int P, int T, int G);
+int dtb_point_in_tet(const float* pos, const int32_t* tet, const float* points, int B, int V, int T, int P, int G,
+                     float* cond, float* bary, void* workspace, size_t workspace_bytes, void* stream);
+int dtb_point_in_tet_soup(const float* tet_bxfx4x3, const float* points, int B, int T, int P, int G, float* cond,
+                          float* bary, void* workspace, size_t workspace_bytes, void* stream);
+int dtb_tet_barycentric_backward(const float* pos, const int32_t* tet, const float* points, const float* cond,
+                                 const float* g_w, int B, int V, int T, int P, float* grad_pos, float* grad_points,
+                                 void* stream);
+
+/* ---- A2: 1-nearest-neighbour index (one-sided chamfer) -----------------------------------------------
+ * Replaces nearest_neighbor_cuda.forward(queries, points, result_int32, batch, nq, np, dim=3)
+ * (layers/nearest_neighbor/nearest_neighbor.cpp:34-52, kernel nearest_neighbor_cuda.cu:17-55):
+ * result (B,Q) i32 = argmin_j |points[b,j] - queries[b,i]|^2, strict <, lowest index wins ties. */
+int dtb_nearest_neighbor_grid_res(int M);
+size_t dtb_nearest_neighbor_workspace(int B, int Q, int M, int G);
+int dtb_nearest_neighbor(const float* queries, const float* points, int32_t* result, int B, int Q, int M, int G,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- device-wide primitives (exported for the self-tests; also usable by integrators) ----------------- */
+size_t dtb_prim_scan_workspace(size_t n);
+int dtb_prim_exclusive_scan_u32(const unsigned* in, unsigned* out, size_t n, unsigned* total, void* ws, size_t ws_bytes,
+                                void* stream);
+size_t dtb_prim_sort_workspace(size_t n);
+int dtb_prim_radix_sort_pairs_u64(unsigned long long* keys_in, unsigned* vals_in, unsigned long long* keys_out,
+                                  unsigned* vals_out, size_t n, int key_bits, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEFTET_B200_H */

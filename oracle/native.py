@@ -1,0 +1,134 @@
+"""numpy front-end of oracle/liboracle.so (C restatement) and oracle/_ref/*/run.so (the reference's own
+ctypes builders compiled from /root/reference).  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py)."""
+import ctypes as C
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle/liboracle.so missing: run `make -C oracle`")
+        _LIB = C.CDLL(path)
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def n_threads():
+    return max(1, os.cpu_count() or 1)
+
+
+def _split(fn, n, threads=None, min_chunk=64):
+    """Run fn(i0, i1) over [0, n) on host threads (ctypes drops the GIL)."""
+    threads = threads or n_threads()
+    chunks = max(1, min(threads * 4, n // min_chunk if n >= min_chunk else 1))
+    bounds = np.linspace(0, n, chunks + 1).astype(np.int64)
+    if chunks == 1 or threads == 1:
+        for k in range(chunks):
+            fn(int(bounds[k]), int(bounds[k + 1]))
+        return
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(lambda k: fn(int(bounds[k]), int(bounds[k + 1])), range(chunks)))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def point_in_tet(tet_bxfx4x3, pts_bxnx3, threads=None):
+    tet, pts = _f32(tet_bxfx4x3), _f32(pts_bxnx3)
+    B, T = tet.shape[0], tet.shape[1]
+    P = pts.shape[1]
+    out = np.full((B, P, 1), -1.0, dtype=np.float32)
+    L = lib()
+    _split(lambda a, b: L.orc_point_in_tet(_p(tet), _p(pts), _p(out), B, P, T, C.c_longlong(a), C.c_longlong(b)), B * P,
+           threads)
+    return out
+
+
+def nearest_neighbor(queries, points, threads=None):
+    q, p = _f32(queries), _f32(points)
+    B, Q, M = q.shape[0], q.shape[1], p.shape[1]
+    out = np.zeros((B, Q), dtype=np.int32)
+    L = lib()
+    _split(lambda a, b: L.orc_nearest_neighbor(_p(q), _p(p), _p(out), B, Q, M, C.c_longlong(a), C.c_longlong(b)), B * Q,
+           threads)
+    return out.astype(np.int64)
+
+
+def point_face_distance(pts, faces, n_face_b=None, threads=None):
+    pts, faces = _f32(pts), _f32(faces)
+    B, P, F = pts.shape[0], pts.shape[1], faces.shape[1]
+    nf = _f32(np.full(B, F) if n_face_b is None else n_face_b)
+    d = np.zeros((B, P, 1), dtype=np.float32)
+    f = np.zeros((B, P, 1), dtype=np.float32)
+    L = lib()
+    _split(lambda a, b: L.orc_point_face_distance(_p(pts), _p(faces), _p(nf), _p(d), _p(f), B, P, F, C.c_longlong(a),
+                                                  C.c_longlong(b)), B * P, threads)
+    return d, f
+
+
+def point_face_distance_bwd(pts, faces, closest_f, dl_dd):
+    pts, faces, cf, g = _f32(pts), _f32(faces), _f32(closest_f), _f32(dl_dd)
+    B, P, F = pts.shape[0], pts.shape[1], faces.shape[1]
+    out = np.zeros((B, F, 3, 3), dtype=np.float32)
+    lib().orc_point_face_distance_bwd(_p(pts), _p(faces), _p(cf), _p(g), _p(out), B, P, F)
+    return out
+
+
+def face_adjacency(face_fx3x3, n_max_nei=30, threads=None):
+    """-> (adj (F, n_max_nei) f32 with -1 padding, pairs (2,E) int64 as utils.py:52-61 builds them)."""
+    face = _f32(face_fx3x3)
+    F = face.shape[0]
+    adj = np.full((F, n_max_nei), -1.0, dtype=np.float32)
+    if F:
+        L = lib()
+        _split(lambda a, b: L.orc_face_adjacency(_p(face), _p(adj), F, n_max_nei, C.c_longlong(a), C.c_longlong(b)), F,
+               threads, min_chunk=16)
+    rows = np.repeat(np.arange(F, dtype=np.int64)[:, None], n_max_nei, axis=1)
+    mask = adj >= 0
+    pairs = np.stack([rows[mask], adj[mask].astype(np.int64)], axis=0)
+    return adj, pairs
+
+
+# ---- the reference's own builders, compiled from /root/reference into oracle/_ref (kind: "reference") ----
+def ref_lib(name):
+    path = os.path.join(HERE, "_ref", name, "run.so")
+    if not os.path.exists(path):
+        return None
+    return C.CDLL(path)
+
+
+def ref_run_tet_builder(name, tet_tx4, n_point, out_rows, out_cols):
+    """Call `run(int* tet, int* out, int* n_out, int n_point, int n_tet)` of utils/lib/<name>/run.cpp."""
+    L = ref_lib(name)
+    if L is None:
+        raise RuntimeError("oracle/_ref/%s/run.so missing (needs /root/reference at build time)" % name)
+    tet = np.ascontiguousarray(tet_tx4, dtype=np.int32)
+    out = np.zeros((out_rows, out_cols), dtype=np.int32)
+    n = np.zeros(1, dtype=np.int32)
+    L.run(_p(tet), _p(out), _p(n), C.c_int(int(n_point)), C.c_int(tet.shape[0]))
+    return out, int(n[0])
+
+
+def ref_colaps_v(points_nx3):
+    L = ref_lib("colaps_v")
+    if L is None:
+        raise RuntimeError("oracle/_ref/colaps_v/run.so missing")
+    pts = _f32(points_nx3)
+    n = pts.shape[0]
+    m = np.zeros(n, dtype=np.int32)
+    inv = np.zeros(n, dtype=np.int32)
+    cnt = np.zeros(1, dtype=np.int32)
+    L.run(_p(pts), _p(m), _p(inv), _p(cnt), C.c_int(n))
+    return m, inv[:cnt[0]]
