@@ -1,0 +1,71 @@
+// Exact nearest-item search over a brick-layout PointGrid: walk cubic shells of 4x4x4-cell bricks outward
+// from the query, skip empty bricks with one 64-bit occupancy word, prune bricks and cells with a
+// conservative lower bound, and hand every surviving item to the visitor.  The visitor keeps the running
+// lexicographic minimum (value, index), so the result equals a brute-force scan in index order with a
+// strict '<' -- the tie rule of every reference search kernel (SURVEY.md section 7 "hard parts").
+#pragma once
+#include "pointgrid.cuh"
+
+namespace dtb {
+
+// squared distance from q to the axis-aligned box [lo, lo + w]^3-ish (per-axis lo, common width w)
+__device__ __forceinline__ float box_dist2(float qx, float qy, float qz, float lx, float ly, float lz, float w, float shrink) {
+    float dx = fmaxf(fmaxf(lx - qx, qx - (lx + w)), 0.f);
+    float dy = fmaxf(fmaxf(ly - qy, qy - (ly + w)), 0.f);
+    float dz = fmaxf(fmaxf(lz - qz, qz - (lz + w)), 0.f);
+    float d = sqrtf(dx * dx + dy * dy + dz * dz);
+    d = fmaxf(d - shrink, 0.f) * 0.9999f;
+    return d * d;
+}
+
+// V must provide:  float bound() const   -- current best value (squared distance) for pruning
+//                  void item(const float4& it)  -- evaluate one item (x,y,z = binned position, w = index bits)
+// `inflate`: radius by which an item may extend beyond the position it was binned with (0 for points).
+template <typename V>
+__device__ __forceinline__ void brick_walk(float qx, float qy, float qz, const GridParams& g, int G, float inflate,
+                                           const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
+                                           const float4* __restrict__ sorted, const unsigned long long* __restrict__ mask,
+                                           size_t cell_base, V& vis) {
+    const int NB = G >> 2;
+    const float bw = 4.0f * g.h;
+    // rounding slack of the cell assignment floor((x-o)*inv_h): a few ulps of the coordinates, far below 1e-3 h
+    const float slack = 1e-3f * g.h + 1e-6f * (fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz) + (float)G * g.h);
+    const float shrink = inflate + slack;
+    const int bx0 = cell_coord(qx, g.ox, g.inv_h, G) >> 2, by0 = cell_coord(qy, g.oy, g.inv_h, G) >> 2,
+              bz0 = cell_coord(qz, g.oz, g.inv_h, G) >> 2;
+    const size_t brick_base = cell_base >> 6;
+    for (int R = 0; R < NB; ++R) {
+        if (R >= 1) {
+            float lb = fmaxf((float)(R - 1) * bw * 0.999f - shrink, 0.f);
+            if (lb * lb > vis.bound()) break;
+        }
+        const int z0 = max(bz0 - R, 0), z1 = min(bz0 + R, NB - 1), y0 = max(by0 - R, 0), y1 = min(by0 + R, NB - 1);
+        for (int bz = z0; bz <= z1; ++bz) {
+            const bool zface = (bz == bz0 - R) || (bz == bz0 + R);
+            for (int by = y0; by <= y1; ++by) {
+                const bool full = zface || (by == by0 - R) || (by == by0 + R);
+                const int xa = max(bx0 - R, 0), xb = min(bx0 + R, NB - 1);
+                const int step = full ? 1 : max(2 * R, 1);
+                for (int bx = bx0 - R; bx <= bx0 + R; bx += step) {
+                    if (bx < xa || bx > xb) continue;
+                    const size_t brick = ((size_t)bz * NB + by) * NB + bx;
+                    unsigned long long m = __ldg(mask + brick_base + brick);
+                    if (!m) continue;
+                    const float lx = g.ox + (float)bx * bw, ly = g.oy + (float)by * bw, lz = g.oz + (float)bz * bw;
+                    if (box_dist2(qx, qy, qz, lx, ly, lz, bw, shrink) > vis.bound()) continue;
+                    const size_t c0 = cell_base + brick * 64;
+                    while (m) {
+                        const int k = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const float cxl = lx + (float)(k & 3) * g.h, cyl = ly + (float)((k >> 2) & 3) * g.h, czl = lz + (float)(k >> 4) * g.h;
+                        if (box_dist2(qx, qy, qz, cxl, cyl, czl, g.h, shrink) > vis.bound()) continue;
+                        const unsigned j0 = __ldg(cell_start + c0 + k), j1 = __ldg(cell_end + c0 + k);
+                        for (unsigned j = j0; j < j1; ++j) vis.item(__ldg(sorted + j));
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace dtb

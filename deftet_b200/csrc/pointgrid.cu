@@ -18,10 +18,11 @@ __global__ void pg_init_kernel(unsigned* bbox_ord, int B) {
     if (i < B * 6) bbox_ord[i] = ((i % 6) < 3) ? 0xffffffffu : 0u;
 }
 
-__global__ void __launch_bounds__(256) pg_bbox_kernel(const float* __restrict__ items, bool tri, int N, unsigned* __restrict__ bbox_ord) {
+__global__ void __launch_bounds__(256) pg_bbox_kernel(const float* __restrict__ items, bool tri, int N, const int32_t* __restrict__ counts, unsigned* __restrict__ bbox_ord) {
     int b = blockIdx.y;
+    const int n = counts ? min(counts[b], N) : N;
     float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float x, y, z;
         load_item(items, (size_t)b * N + i, tri, x, y, z);
         if (x == x && y == y && z == z) {
@@ -52,32 +53,50 @@ __global__ void pg_fix_bbox_kernel(unsigned* bbox_ord, int B) {
     }
 }
 
-__global__ void __launch_bounds__(256) pg_count_kernel(const float* __restrict__ items, bool tri, int N, int G,
-                                                       const unsigned* __restrict__ bbox_ord, unsigned* __restrict__ cell_count,
+__global__ void __launch_bounds__(256) pg_count_kernel(const float* __restrict__ items, bool tri, int N, int G, bool brick,
+                                                       const int32_t* __restrict__ counts, const unsigned* __restrict__ bbox_ord, unsigned* __restrict__ cell_count,
                                                        unsigned* __restrict__ cell_of) {
     int b = blockIdx.y;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    if (i >= N || (counts && i >= counts[b])) return;
     GridParams g = grid_params(bbox_ord, b, G);
     float x, y, z;
     load_item(items, (size_t)b * N + i, tri, x, y, z);
     int cx = cell_coord(x, g.ox, g.inv_h, G), cy = cell_coord(y, g.oy, g.inv_h, G), cz = cell_coord(z, g.oz, g.inv_h, G);
-    unsigned c = ((unsigned)b * G + cz) * G * G + cy * G + cx;
+    unsigned c = (unsigned)b * G * G * G + cell_index(cx, cy, cz, G, brick);
     cell_of[(size_t)b * N + i] = c;
     atomicAdd(&cell_count[c], 1u);
 }
 
-__global__ void __launch_bounds__(256) pg_fill_kernel(const float* __restrict__ items, bool tri, int N,
+__global__ void __launch_bounds__(256) pg_fill_kernel(const float* __restrict__ items, bool tri, int N, const int32_t* __restrict__ counts,
                                                       const unsigned* __restrict__ cell_of, unsigned* __restrict__ cell_end,
                                                       float4* __restrict__ sorted) {
     int b = blockIdx.y;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    if (i >= N || (counts && i >= counts[b])) return;
     float x, y, z;
     load_item(items, (size_t)b * N + i, tri, x, y, z);
     unsigned c = cell_of[(size_t)b * N + i];
     unsigned dst = atomicAdd(&cell_end[c], 1u);
     sorted[dst] = make_float4(x, y, z, __int_as_float(i));
+}
+
+__global__ void pg_brick_mask_kernel(const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end, size_t n_bricks,
+                                     unsigned long long* __restrict__ mask) {
+    size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_bricks) return;
+    unsigned long long m = 0;
+    const uint4* s4 = reinterpret_cast<const uint4*>(cell_start + w * 64);
+    const uint4* e4 = reinterpret_cast<const uint4*>(cell_end + w * 64);
+#pragma unroll 4
+    for (int k = 0; k < 16; ++k) {
+        uint4 s = s4[k], e = e4[k];
+        if (e.x > s.x) m |= 1ull << (4 * k);
+        if (e.y > s.y) m |= 1ull << (4 * k + 1);
+        if (e.z > s.z) m |= 1ull << (4 * k + 2);
+        if (e.w > s.w) m |= 1ull << (4 * k + 3);
+    }
+    mask[w] = m;
 }
 
 __global__ void pg_mask_kernel(const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end, int G, int W,
@@ -94,28 +113,30 @@ __global__ void pg_mask_kernel(const unsigned* __restrict__ cell_start, const un
     mask[w] = m;
 }
 
-size_t pointgrid_workspace_bytes(int B, int N, int G, bool with_mask) {
+size_t pointgrid_workspace_bytes(int B, int N, int G, bool with_mask, bool brick) {
     Workspace ws(nullptr, 0);
     PointGrid pg;
-    pointgrid_carve(pg, B, N, G, with_mask, ws);
+    pointgrid_carve(pg, B, N, G, with_mask, brick, ws);
     return ws.off;
 }
 
-bool pointgrid_carve(PointGrid& pg, int B, int N, int G, bool with_mask, Workspace& ws) {
-    pg.B = B; pg.N = N; pg.G = G; pg.W = (G + 63) / 64;
+bool pointgrid_carve(PointGrid& pg, int B, int N, int G, bool with_mask, bool brick, Workspace& ws) {
+    pg.B = B; pg.N = N; pg.G = G; pg.W = (G + 63) / 64; pg.brick = brick;
     size_t cells = (size_t)B * G * G * G;
     pg.bbox_ord = ws.take<unsigned>((size_t)B * 6);
     pg.cell_start = ws.take<unsigned>(cells);
     pg.cell_end = ws.take<unsigned>(cells);
     pg.sorted = ws.take<float4>((size_t)B * N);
     pg.cell_of = ws.take<unsigned>((size_t)B * N);
-    pg.mask = with_mask ? ws.take<unsigned long long>((size_t)B * G * G * pg.W) : nullptr;
+    pg.mask = with_mask ? ws.take<unsigned long long>(brick ? cells / 64 : (size_t)B * G * G * pg.W) : nullptr;
     pg.scan_ws_bytes = scan_workspace_bytes(cells);
     pg.scan_ws = ws.take<char>(pg.scan_ws_bytes);
     return ws.ok;
 }
 
-int pointgrid_build(PointGrid& pg, const float* items, bool tri, cudaStream_t st) {
+int pointgrid_build(PointGrid& pg, const float* items, bool tri, cudaStream_t st) { return pointgrid_build_ragged(pg, items, tri, nullptr, st); }
+
+int pointgrid_build_ragged(PointGrid& pg, const float* items, bool tri, const int32_t* counts, cudaStream_t st) {
     const int B = pg.B, N = pg.N, G = pg.G;
     size_t cells = (size_t)B * G * G * G;
     if (cells >= (1ull << 31) || (size_t)B * N >= (1ull << 31)) { set_error("pointgrid: problem too large for 32-bit cell ids"); return DTB_EOVERFLOW; }
@@ -123,15 +144,15 @@ int pointgrid_build(PointGrid& pg, const float* items, bool tri, cudaStream_t st
     DTB_LAUNCH_CHECK("pg_init");
     DTB_CUDA(cudaMemsetAsync(pg.cell_start, 0, cells * sizeof(unsigned), st));
     if (N > 0) {
-        dim3 gb(min(cdiv(N, 256), 64), B);
-        pg_bbox_kernel<<<gb, 256, 0, st>>>(items, tri, N, pg.bbox_ord);
+        dim3 gb(min(cdiv(N, 256 * 4), 256), B);
+        pg_bbox_kernel<<<gb, 256, 0, st>>>(items, tri, N, counts, pg.bbox_ord);
         DTB_LAUNCH_CHECK("pg_bbox");
     }
     pg_fix_bbox_kernel<<<cdiv(B, 128), 128, 0, st>>>(pg.bbox_ord, B);
     DTB_LAUNCH_CHECK("pg_fix_bbox");
     if (N > 0) {
         dim3 gc(cdiv(N, 256), B);
-        pg_count_kernel<<<gc, 256, 0, st>>>(items, tri, N, G, pg.bbox_ord, pg.cell_start, pg.cell_of);
+        pg_count_kernel<<<gc, 256, 0, st>>>(items, tri, N, G, pg.brick, counts, pg.bbox_ord, pg.cell_start, pg.cell_of);
         DTB_LAUNCH_CHECK("pg_count");
     }
     int rc = exclusive_scan_u32(pg.cell_start, pg.cell_start, cells, nullptr, pg.scan_ws, pg.scan_ws_bytes, st);
@@ -139,10 +160,15 @@ int pointgrid_build(PointGrid& pg, const float* items, bool tri, cudaStream_t st
     DTB_CUDA(cudaMemcpyAsync(pg.cell_end, pg.cell_start, cells * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
     if (N > 0) {
         dim3 gc(cdiv(N, 256), B);
-        pg_fill_kernel<<<gc, 256, 0, st>>>(items, tri, N, pg.cell_of, pg.cell_end, pg.sorted);
+        pg_fill_kernel<<<gc, 256, 0, st>>>(items, tri, N, counts, pg.cell_of, pg.cell_end, pg.sorted);
         DTB_LAUNCH_CHECK("pg_fill");
     }
-    if (pg.mask) {
+    if (pg.brick && (G % 4) != 0) { set_error("pointgrid: brick layout needs G %% 4 == 0 (G=%d)", G); return DTB_EINVAL; }
+    if (pg.mask && pg.brick) {
+        size_t n_bricks = cells / 64;
+        pg_brick_mask_kernel<<<cdiv((long long)n_bricks, 128), 128, 0, st>>>(pg.cell_start, pg.cell_end, n_bricks, pg.mask);
+        DTB_LAUNCH_CHECK("pg_brick_mask");
+    } else if (pg.mask) {
         size_t n_words = (size_t)B * G * G * pg.W;
         pg_mask_kernel<<<cdiv((long long)n_words, 256), 256, 0, st>>>(pg.cell_start, pg.cell_end, G, pg.W, n_words, pg.mask);
         DTB_LAUNCH_CHECK("pg_mask");

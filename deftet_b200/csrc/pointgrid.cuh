@@ -5,7 +5,8 @@
 //   bbox_ord [B][6]            order-preserving-encoded min xyz / max xyz of the items
 //   cell_start/cell_end [B*G^3] item range of each cell inside `sorted`
 //   sorted  [B*N] float4       (x, y, z, original index as int bits), grouped by cell
-//   mask    [B*G*G*W] u64      occupancy bits along x (W = ceil(G/64) words per row), optional
+//   mask    u64 occupancy words, optional: row-major layout -> [B*G*G*W] bits along x (W = ceil(G/64));
+//           brick layout -> [B*(G/4)^3], bit (z&3)*16+(y&3)*4+(x&3) of the brick's word
 // Cell of x on one axis: clamp(floor((x - min) * inv_h), 0, G-1), inv_h = G / (max extent * (1 + 2^-20)):
 // monotone in x, so conservative cell ranges of boxes are obtained by mapping their corners.
 #pragma once
@@ -21,6 +22,7 @@ struct GridParams {     // per-sample, computed on device from bbox_ord
 
 struct PointGrid {
     int B, N, G, W;
+    bool brick;               // cell order: false = row-major (z,y,x); true = 4x4x4 bricks (G % 4 == 0), 64 cells per brick
     unsigned* bbox_ord;       // [B][6]
     unsigned* cell_start;     // [B*G^3]
     unsigned* cell_end;       // [B*G^3]
@@ -41,17 +43,26 @@ __device__ __forceinline__ GridParams grid_params(const unsigned* bbox_ord, int 
     g.h = ext / (float)G;
     return g;
 }
+// linear cell id inside one sample
+__device__ __forceinline__ unsigned cell_index(int cx, int cy, int cz, int G, bool brick) {
+    if (!brick) return ((unsigned)cz * G + cy) * G + cx;
+    unsigned nb = (unsigned)G >> 2;
+    unsigned bid = (((unsigned)cz >> 2) * nb + ((unsigned)cy >> 2)) * nb + ((unsigned)cx >> 2);
+    return bid * 64u + ((cz & 3) << 4) + ((cy & 3) << 2) + (cx & 3);
+}
 __device__ __forceinline__ int cell_coord(float x, float o, float inv_h, int G) {
     float f = floorf((x - o) * inv_h);
     f = fminf(fmaxf(f, 0.0f), (float)(G - 1));      // NaN -> 0
     return (int)f;
 }
 
-size_t pointgrid_workspace_bytes(int B, int N, int G, bool with_mask);
+size_t pointgrid_workspace_bytes(int B, int N, int G, bool with_mask, bool brick);
 // carve a PointGrid out of ws (returns false if it does not fit)
-bool pointgrid_carve(PointGrid& pg, int B, int N, int G, bool with_mask, Workspace& ws);
+bool pointgrid_carve(PointGrid& pg, int B, int N, int G, bool with_mask, bool brick, Workspace& ws);
 // enqueue: bbox -> count -> scan -> fill (-> mask).  items: (B,N,3) f32 contiguous, or, when
 // `tri_centroid` is true, (B,N,3,3) triangles binned by centroid.
 int pointgrid_build(PointGrid& pg, const float* items, bool tri_centroid, cudaStream_t st);
+// same, but only the first counts[b] items of sample b exist (padded-ragged batches)
+int pointgrid_build_ragged(PointGrid& pg, const float* items, bool tri_centroid, const int32_t* counts, cudaStream_t st);
 
 }  // namespace dtb

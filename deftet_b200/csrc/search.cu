@@ -12,7 +12,7 @@
 //       keeps the lexicographic minimum of (distance, index) -> "strict <, lowest index wins" exactly.
 // Predicates and distances use the non-contracted fp32 sequence of the reference source (common.cuh x*),
 // so indices are bit-identical to the CPU oracle.
-#include "pointgrid.cuh"
+#include "brickwalk.cuh"
 #include "deftet_b200.h"
 
 namespace dtb {
@@ -205,67 +205,33 @@ __global__ void __launch_bounds__(256) bary_backward_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------------------
 // A2
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) nn_query_kernel(const float* __restrict__ queries, int Q, int G, int W,
+struct NnVisitor {
+    float qx, qy, qz;
+    float best;      // nearest_neighbor_cuda.cu:28-29: min_distance = 1e20, min_point = 0
+    int bi;
+    __device__ __forceinline__ float bound() const { return best; }
+    __device__ __forceinline__ void item(const float4& p) {
+        float dx = xsub(p.x, qx), dy = xsub(p.y, qy), dz = xsub(p.z, qz);
+        float d = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
+        int idx = __float_as_int(p.w);
+        if (d < best || (d == best && idx < bi)) { best = d; bi = idx; }
+    }
+};
+
+__global__ void __launch_bounds__(128) nn_query_kernel(const float* __restrict__ queries, int Q, int G,
                                                        const unsigned* __restrict__ bbox_ord, const unsigned* __restrict__ cell_start,
                                                        const unsigned* __restrict__ cell_end, const float4* __restrict__ sorted,
-                                                       const unsigned long long* __restrict__ mask, int* __restrict__ result) {
+                                                       const unsigned long long* __restrict__ mask, int* __restrict__ result,
+                                                       const int32_t* __restrict__ q_counts, int q_mult) {
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Q) return;
+    if (q_counts && i >= q_counts[b] * q_mult) return;
     const float* qp = queries + ((size_t)b * Q + i) * 3;
-    const float qx = qp[0], qy = qp[1], qz = qp[2];
+    NnVisitor v{qp[0], qp[1], qp[2], 1e20f, 0};
     GridParams g = grid_params(bbox_ord, b, G);
-    const int cx = cell_coord(qx, g.ox, g.inv_h, G), cy = cell_coord(qy, g.oy, g.inv_h, G), cz = cell_coord(qz, g.oz, g.inv_h, G);
-    float best = 1e20f;      // nearest_neighbor_cuda.cu:28-29
-    int bi = 0;
-    const size_t cbase = (size_t)b * G * G * G;
-    const size_t mbase = (size_t)b * G * G * W;
-    for (int r = 0; r < G; ++r) {
-        if (r >= 1) {
-            float lb = (float)(r - 1) * g.h * 0.999f;      // every point of shell r is at least this far (conservative)
-            if (lb * lb > best) break;
-        }
-        int z0 = max(cz - r, 0), z1 = min(cz + r, G - 1), y0 = max(cy - r, 0), y1 = min(cy + r, G - 1);
-        int xa = cx - r, xb = cx + r;
-        for (int z = z0; z <= z1; ++z) {
-            bool zface = (z == cz - r) || (z == cz + r);
-            for (int y = y0; y <= y1; ++y) {
-                bool full = zface || (y == cy - r) || (y == cy + r);
-                const unsigned long long* mrow = mask + mbase + ((size_t)z * G + y) * W;
-                size_t row = cbase + ((size_t)z * G + y) * G;
-                for (int w = 0; w < W; ++w) {
-                    int lo = w * 64;
-                    unsigned long long sel;
-                    if (full) {
-                        int a = max(xa, lo), e = min(xb, lo + 63);
-                        if (a > e) continue;
-                        int n = e - a + 1;
-                        sel = (n >= 64 ? ~0ull : ((1ull << n) - 1ull)) << (a - lo);
-                    } else {
-                        sel = 0ull;
-                        if (xa >= lo && xa < lo + 64) sel |= 1ull << (xa - lo);
-                        if (xb >= lo && xb < lo + 64 && xb < G) sel |= 1ull << (xb - lo);
-                        if (!sel) continue;
-                    }
-                    unsigned long long m = __ldg(mrow + w) & sel;
-                    while (m) {
-                        int k = __ffsll((long long)m) - 1;
-                        m &= m - 1;
-                        size_t c = row + lo + k;
-                        unsigned j0 = cell_start[c], j1 = cell_end[c];
-                        for (unsigned j = j0; j < j1; ++j) {
-                            float4 p = __ldg(sorted + j);
-                            float dx = xsub(p.x, qx), dy = xsub(p.y, qy), dz = xsub(p.z, qz);
-                            float d = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
-                            int idx = __float_as_int(p.w);
-                            if (d < best || (d == best && idx < bi)) { best = d; bi = idx; }
-                        }
-                    }
-                }
-            }
-        }
-    }
-    result[(size_t)b * Q + i] = bi;
+    brick_walk(v.qx, v.qy, v.qz, g, G, 0.0f, cell_start, cell_end, sorted, mask, (size_t)b * G * G * G, v);
+    result[(size_t)b * Q + i] = v.bi;
 }
 
 }  // namespace dtb
@@ -286,7 +252,7 @@ extern "C" int dtb_point_in_tet_grid_res(int T, int P) {
 }
 extern "C" size_t dtb_point_in_tet_workspace(int B, int P, int T, int G) {
     if (G <= 0) G = dtb_point_in_tet_grid_res(T, P);
-    return pointgrid_workspace_bytes(B, P, G, false) + align_up((size_t)B * P * sizeof(int), 256);
+    return pointgrid_workspace_bytes(B, P, G, false, false) + align_up((size_t)B * P * sizeof(int), 256);
 }
 
 template <typename Src>
@@ -297,7 +263,7 @@ static int point_in_tet_impl(Src src, const float* points, int B, int T, int P, 
     if (G <= 0) G = dtb_point_in_tet_grid_res(T, P);
     Workspace ws(workspace, workspace_bytes);
     PointGrid pg;
-    pointgrid_carve(pg, B, P, G, false, ws);
+    pointgrid_carve(pg, B, P, G, false, false, ws);
     int* hit = ws.take<int>((size_t)B * P);
     if (!ws.ok || !workspace) { set_error("point_in_tet: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return DTB_EWORKSPACE; }
     int rc = pointgrid_build(pg, points, false, st);
@@ -343,7 +309,8 @@ extern "C" int dtb_tet_barycentric_backward(const float* pos, const int32_t* tet
 // ---- A2 -------------------------------------------------------------------------------------------
 extern "C" int dtb_nearest_neighbor_grid_res(int M) {
     // target points usually sample a surface: ~M^(1/2) cells per axis keeps a few points per occupied cell
-    int g = (int)ceil(sqrt((double)(M > 1 ? M : 1)) * 0.35);
+    int g = (int)ceil(sqrt((double)(M > 1 ? M : 1)) * 0.2);
+    g = (g + 3) / 4 * 4;                 // brick layout: multiple of 4
     if (g < 4) g = 4;
     if (g > 128) g = 128;
     return g;
@@ -351,10 +318,11 @@ extern "C" int dtb_nearest_neighbor_grid_res(int M) {
 extern "C" size_t dtb_nearest_neighbor_workspace(int B, int Q, int M, int G) {
     (void)Q;
     if (G <= 0) G = dtb_nearest_neighbor_grid_res(M);
-    return pointgrid_workspace_bytes(B, M, G, true);
+    G = (G + 3) / 4 * 4;
+    return pointgrid_workspace_bytes(B, M, G, true, true);
 }
-extern "C" int dtb_nearest_neighbor(const float* queries, const float* points, int32_t* result, int B, int Q, int M, int G,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+static int nearest_neighbor_impl(const float* queries, const float* points, int32_t* result, int B, int Q, int M, int G,
+                                 const int32_t* q_counts, int q_mult, void* workspace, size_t workspace_bytes, void* stream) {
     DTB_REQUIRE(B > 0 && Q >= 0 && M >= 0, "nearest_neighbor: bad sizes");
     if (Q == 0) return DTB_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -364,14 +332,28 @@ extern "C" int dtb_nearest_neighbor(const float* queries, const float* points, i
         return DTB_OK;
     }
     if (G <= 0) G = dtb_nearest_neighbor_grid_res(M);
+    G = (G + 3) / 4 * 4;
     Workspace ws(workspace, workspace_bytes);
     PointGrid pg;
-    pointgrid_carve(pg, B, M, G, true, ws);
+    pointgrid_carve(pg, B, M, G, true, true, ws);
     if (!ws.ok || !workspace) { set_error("nearest_neighbor: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return DTB_EWORKSPACE; }
     int rc = pointgrid_build(pg, points, false, st);
     if (rc) return rc;
     dim3 grid(cdiv(Q, 128), B);
-    nn_query_kernel<<<grid, 128, 0, st>>>(queries, Q, G, pg.W, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask, result);
+    nn_query_kernel<<<grid, 128, 0, st>>>(queries, Q, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask, result, q_counts, q_mult);
     DTB_LAUNCH_CHECK("nn_query");
     return DTB_OK;
+}
+
+extern "C" int dtb_nearest_neighbor(const float* queries, const float* points, int32_t* result, int B, int Q, int M, int G,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    return nearest_neighbor_impl(queries, points, result, B, Q, M, G, nullptr, 1, workspace, workspace_bytes, stream);
+}
+
+// padded-ragged queries: only the first q_counts[b] * q_mult queries of sample b are answered
+extern "C" int dtb_nearest_neighbor_ragged(const float* queries, const int32_t* q_counts, int q_mult, const float* points,
+                                           int32_t* result, int B, int Qmax, int M, int G, void* workspace, size_t workspace_bytes,
+                                           void* stream) {
+    DTB_REQUIRE(q_counts != nullptr, "nearest_neighbor_ragged: null q_counts");
+    return nearest_neighbor_impl(queries, points, result, B, Qmax, M, G, q_counts, q_mult, workspace, workspace_bytes, stream);
 }

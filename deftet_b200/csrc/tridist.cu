@@ -1,0 +1,357 @@
+// A4: point -> triangle-set squared distance, forward and backward.
+//   forward   reference layers/DefTet/tet_analytic_distance_batch/tet_analytic_distance_for.cu:139-307
+//   backward  reference layers/DefTet/tet_analytic_distance_batch/tet_analytic_distance_back.cu:222-317,348-483,592-686
+// The reference tests every point against every face (O(S*F)).  Here the faces are binned by centroid into
+// a brick grid and each point walks outwards with the bound  dist(point, cell box) - R_max, R_max = largest
+// centroid-to-vertex distance of the sample, evaluating the reference's exact (non-contracted fp32)
+// triangle-distance expression only on the surviving faces and keeping the lexicographic minimum
+// (distance, face id) = "first strict minimum" of the reference.  The reference distance is the true
+// point-triangle distance except that its inside test is done on the xy-projection: faces whose normal is
+// (almost) horizontal can be mis-classified, so they are not pruned geometrically but kept on a short
+// per-sample "always test" list; faces with k3 == 0 exactly are invisible to the reference (:176-183) and
+// stay invisible here.  All reference quirks (edge-case gradient overwrite at _back.cu:309-315, MAX_DIS
+// sentinels) are reproduced.
+#include "brickwalk.cuh"
+#include "deftet_b200.h"
+
+namespace dtb {
+
+constexpr float FWD_MAX_DIS = 10000.0f;     // tet_analytic_distance_for.cu:17
+constexpr float BWD_MAX_DIS = 9999999.0f;   // tet_analytic_distance_back.cu:19
+
+// cuda_divide_non_zero: `a + eps` with a double eps is evaluated in double and narrowed on return
+__device__ __forceinline__ float div_nz(float a) {
+    if (a == 0.f) return (float)1e-10;
+    if (a < 0.f) return (float)((double)a - 1e-10);
+    if (a > 0.f) return (float)((double)a + 1e-10);
+    return (float)1e-10;
+}
+__device__ __forceinline__ float xdot(const float* a, const float* b) { return xadd(xadd(xmul(a[0], b[0]), xmul(a[1], b[1])), xmul(a[2], b[2])); }
+__device__ __forceinline__ float xmin3(float a, float b, float c) { float m = a; if (b < m) m = b; if (c < m) m = c; return m; }
+__device__ __forceinline__ int xmin3_idx(float a, float b, float c) { float m = a; int i = 0; if (b < m) { m = b; i = 1; } if (c < m) { m = c; i = 2; } return i; }
+__device__ __forceinline__ float xabs(float a) { return a > 0.0f ? a : -a; }
+__device__ __forceinline__ float pt_dist2(const float* a, const float* p) {
+    float e0 = xsub(a[0], p[0]), e1 = xsub(a[1], p[1]), e2 = xsub(a[2], p[2]);
+    return xadd(xadd(xmul(e0, e0), xmul(e1, e1)), xmul(e2, e2));
+}
+// distance_line_square: negative when the foot point is outside the segment
+__device__ __forceinline__ float line_dist2(const float* A, const float* B, const float* P, float* t_out) {
+    float PA[3] = {xsub(P[0], A[0]), xsub(P[1], A[1]), xsub(P[2], A[2])};
+    float BA[3] = {xsub(B[0], A[0]), xsub(B[1], A[1]), xsub(B[2], A[2])};
+    float t = xdiv(xdot(PA, BA), div_nz(xdot(BA, BA)));
+    float d[3] = {xsub(PA[0], xmul(BA[0], t)), xsub(PA[1], xmul(BA[1], t)), xsub(PA[2], xmul(BA[2], t))};
+    float dist = xdot(d, d);
+    if (t_out) *t_out = t;
+    return (t >= 0.f && t <= 1.f) ? dist : -dist;
+}
+
+struct TriHit { int type; float plane2; float inplane; int idx; float ip[3]; float l1, l2, l3; };
+
+// cuda_min_triangle_distance + cuda_line_distance.  Returns the reference distance; fills hit.
+__device__ __forceinline__ float tri_distance(const float* a, const float* b, const float* c, const float* p, float max_dis, TriHit& h) {
+    float r1[3] = {xsub(b[0], a[0]), xsub(b[1], a[1]), xsub(b[2], a[2])};
+    float r2[3] = {xsub(c[0], a[0]), xsub(c[1], a[1]), xsub(c[2], a[2])};
+    float n[3] = {xsub(xmul(r1[1], r2[2]), xmul(r1[2], r2[1])), xsub(xmul(r1[2], r2[0]), xmul(r1[0], r2[2])),
+                  xsub(xmul(r1[0], r2[1]), xmul(r1[1], r2[0]))};
+    float len = div_nz(xsqrt(xadd(xadd(xmul(n[0], n[0]), xmul(n[1], n[1])), xmul(n[2], n[2]))));
+    n[0] = xdiv(n[0], len); n[1] = xdiv(n[1], len); n[2] = xdiv(n[2], len);
+    float t = xsub(xdot(n, a), xdot(n, p));
+    float ip[3] = {xadd(p[0], xmul(n[0], t)), xadd(p[1], xmul(n[1], t)), xadd(p[2], xmul(n[2], t))};
+    h.ip[0] = ip[0]; h.ip[1] = ip[1]; h.ip[2] = ip[2];
+    h.plane2 = xmul(t, t);
+    h.idx = 0; h.inplane = 0.f;
+    // xy-projected barycentric test
+    float k1 = xadd(xmul(xsub(b[1], c[1]), xsub(ip[0], c[0])), xmul(xsub(c[0], b[0]), xsub(ip[1], c[1])));
+    float k2 = xadd(xmul(xsub(a[0], c[0]), xsub(ip[1], c[1])), xmul(xsub(c[1], a[1]), xsub(ip[0], c[0])));
+    float k3 = xadd(xmul(xsub(b[1], c[1]), xsub(a[0], c[0])), xmul(xsub(c[0], b[0]), xsub(a[1], c[1])));
+    if (k3 == 0.f) { h.type = -1; return max_dis; }
+    float l1 = xdiv(k1, k3), l2 = xdiv(k2, k3), l3 = xsub(xsub(1.0f, l1), l2);
+    h.l1 = l1; h.l2 = l2; h.l3 = l3;
+    float d12 = line_dist2(a, b, ip, nullptr), d23 = line_dist2(b, c, ip, nullptr), d13 = line_dist2(a, c, ip, nullptr);
+    if (l1 >= 0.f && l2 >= 0.f && l3 >= 0.f) {
+        h.type = 0;
+        h.inplane = xmin3(xabs(d12), xabs(d23), xabs(d13));
+        h.idx = xmin3_idx(xabs(d12), xabs(d23), xabs(d13));
+        return h.plane2;
+    }
+    if (d12 <= 0.f) d12 = max_dis;
+    if (d23 <= 0.f) d23 = max_dis;
+    if (d13 <= 0.f) d13 = max_dis;
+    float ml = xmin3(d12, d23, d13);
+    int mli = xmin3_idx(d12, d23, d13);
+    float e1 = pt_dist2(a, ip), e2 = pt_dist2(b, ip), e3 = pt_dist2(c, ip);
+    float mp = xmin3(e1, e2, e3);
+    int mpi = xmin3_idx(e1, e2, e3);
+    if (ml < mp) { h.type = 1; h.inplane = ml; h.idx = mli; }
+    else { h.type = 2; h.inplane = mp; h.idx = mpi; }
+    return xadd(h.plane2, h.inplane);
+}
+
+// ---- per-sample face statistics: R_max and the "always test" list ---------------------------------------
+__global__ void __launch_bounds__(256) face_stats_kernel(const float* __restrict__ soup, const int32_t* __restrict__ counts, int Fmax,
+                                                         unsigned* __restrict__ rmax_bits, int32_t* __restrict__ always,
+                                                         int32_t* __restrict__ n_always, int always_cap) {
+    int b = blockIdx.y;
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    float r = 0.f;
+    if (f < counts[b]) {
+        const float* t = soup + ((size_t)b * Fmax + f) * 9;
+        float cx = (t[0] + t[3] + t[6]) * (1.f / 3.f), cy = (t[1] + t[4] + t[7]) * (1.f / 3.f), cz = (t[2] + t[5] + t[8]) * (1.f / 3.f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float dx = t[k * 3] - cx, dy = t[k * 3 + 1] - cy, dz = t[k * 3 + 2] - cz;
+            r = fmaxf(r, sqrtf(dx * dx + dy * dy + dz * dz));
+        }
+        float e1[3] = {t[3] - t[0], t[4] - t[1], t[5] - t[2]}, e2[3] = {t[6] - t[0], t[7] - t[1], t[8] - t[2]};
+        float nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
+        float nn = sqrtf(nx * nx + ny * ny + nz * nz);
+        // xy-projection unreliable (or not a finite triangle): never prune this face geometrically
+        bool unreliable = !(fabsf(nz) > 1e-3f * nn) || !(r == r) || !(nn == nn);
+        if (unreliable) {
+            int k = atomicAdd(n_always + b, 1);
+            if (k < always_cap) always[(size_t)b * always_cap + k] = f;
+        }
+        if (!(r == r)) r = 0.f;
+    }
+    r = warp_max(r);
+    if ((threadIdx.x & 31) == 0 && r > 0.f) atomicMax(rmax_bits + b, __float_as_uint(r));
+}
+
+struct TriVisitor {
+    const float* soup;      // this sample's (Fmax,3,3)
+    float p[3];
+    float best; int bi;
+    __device__ __forceinline__ float bound() const { return best; }
+    __device__ __forceinline__ void face(int f) {
+        const float* t = soup + (size_t)f * 9;
+        float a[3] = {__ldg(t), __ldg(t + 1), __ldg(t + 2)}, b[3] = {__ldg(t + 3), __ldg(t + 4), __ldg(t + 5)},
+              c[3] = {__ldg(t + 6), __ldg(t + 7), __ldg(t + 8)};
+        TriHit h;
+        float d = tri_distance(a, b, c, p, FWD_MAX_DIS, h);
+        if (best > d || (d == best && bi >= 0 && f < bi)) { best = d; bi = f; }
+    }
+    __device__ __forceinline__ void item(const float4& it) { face(__float_as_int(it.w)); }
+};
+
+__global__ void __launch_bounds__(128) pfd_forward_kernel(const float* __restrict__ points, int S, const float* __restrict__ soup,
+                                                          const int32_t* __restrict__ counts, int Fmax, int G,
+                                                          const unsigned* __restrict__ bbox_ord, const unsigned* __restrict__ cell_start,
+                                                          const unsigned* __restrict__ cell_end, const float4* __restrict__ sorted,
+                                                          const unsigned long long* __restrict__ mask,
+                                                          const unsigned* __restrict__ rmax_bits, const int32_t* __restrict__ always,
+                                                          const int32_t* __restrict__ n_always, int always_cap,
+                                                          float* __restrict__ closest_d, float* __restrict__ closest_f) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const float* pp = points + ((size_t)b * S + i) * 3;
+    TriVisitor v;
+    v.soup = soup + (size_t)b * Fmax * 9;
+    v.p[0] = pp[0]; v.p[1] = pp[1]; v.p[2] = pp[2];
+    v.best = 10000.0f; v.bi = -1;              // tet_analytic_distance_for.cu:278-279
+    const int nf = counts[b];
+    const int na = n_always[b];
+    if (na > always_cap) {                     // too many unreliable faces: exact brute force for this sample
+        for (int f = 0; f < nf; ++f) v.face(f);
+    } else if (nf > 0) {
+        for (int k = 0; k < na; ++k) v.face(always[(size_t)b * always_cap + k]);
+        GridParams g = grid_params(bbox_ord, b, G);
+        float rmax = __uint_as_float(rmax_bits[b]);
+        brick_walk(v.p[0], v.p[1], v.p[2], g, G, rmax * 1.001f, cell_start, cell_end, sorted, mask, (size_t)b * G * G * G, v);
+    }
+    closest_d[(size_t)b * S + i] = v.best;
+    closest_f[(size_t)b * S + i] = (float)v.bi;
+}
+
+// ---- backward ---------------------------------------------------------------------------------------
+// grads (3x3) of the reference distance w.r.t. the vertices of the closest face, times `scale`
+__device__ __forceinline__ void tri_grad(const float* face, const float* p, float scale, float* g9) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g9[k] = 0.f;
+    TriHit h;
+    tri_distance(face, face + 3, face + 6, p, BWD_MAX_DIS, h);
+    if (h.type == 0) {                  // cuda_gradient_triangle_distance (_back.cu:440-483)
+        float l[3] = {h.l1, h.l2, h.l3};
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) g9[v * 3 + k] = scale * (2.f * (h.ip[k] - p[k]) * l[v]);
+    } else if (h.type == 1) {           // cuda_gradient_line_distance (_back.cu:291-317): grad[0..2] overwritten with the *t term
+        int i1 = h.idx;
+        int i2 = (i1 + 1) % 3;
+        const float* A = face + i1 * 3;
+        const float* B = face + i2 * 3;
+        float PA[3] = {xsub(p[0], A[0]), xsub(p[1], A[1]), xsub(p[2], A[2])};
+        float BA[3] = {xsub(B[0], A[0]), xsub(B[1], A[1]), xsub(B[2], A[2])};
+        float t = xdiv(xdot(PA, BA), div_nz(xdot(BA, BA)));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float q = A[k] * (1.f - t) + B[k] * t;
+            g9[i1 * 3 + k] = scale * (2.f * (q - p[k]) * t);
+        }
+    } else if (h.type == 2) {
+        int iv = h.idx;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g9[iv * 3 + k] = 2.f * scale * (face[iv * 3 + k] - p[k]);
+    }
+}
+
+// drop-in: atomics into dldface (B,F,3,3), upstream dl_dd (B,S)
+__global__ void __launch_bounds__(256) pfd_backward_kernel(const float* __restrict__ points, int S, const float* __restrict__ soup, int Fmax,
+                                                           const float* __restrict__ closest_f, const float* __restrict__ dl_dd,
+                                                           float* __restrict__ dldface) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    size_t o = (size_t)b * S + i;
+    int f = (int)closest_f[o];
+    if (f < 0 || f >= Fmax) return;                 // the reference would read out of bounds for -1
+    const float* face = soup + ((size_t)b * Fmax + f) * 9;
+    float fc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) fc[k] = face[k];
+    float p[3] = {points[o * 3], points[o * 3 + 1], points[o * 3 + 2]};
+    float g9[9];
+    tri_grad(fc, p, dl_dd[o], g9);
+    float* g = dldface + ((size_t)b * Fmax + f) * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+        if (g9[k] != 0.f) atomicAdd(g + k, g9[k]);
+}
+
+// engine: loss_b = mean_i sqrt(d_i + 1e-10) (mesh_utils.py:373, deftet.py:181); scatter straight to grad_pos
+__global__ void __launch_bounds__(256) pfd_backward_indexed_kernel(const float* __restrict__ points, int S, const float* __restrict__ soup,
+                                                                   const int32_t* __restrict__ faces, int Fmax, int V,
+                                                                   const float* __restrict__ closest_f, const float* __restrict__ closest_d,
+                                                                   const float* __restrict__ g_loss, float* __restrict__ grad_pos) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    size_t o = (size_t)b * S + i;
+    int f = (int)closest_f[o];
+    if (f < 0 || f >= Fmax) return;
+    const float* face = soup + ((size_t)b * Fmax + f) * 9;
+    float fc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) fc[k] = face[k];
+    float p[3] = {points[o * 3], points[o * 3 + 1], points[o * 3 + 2]};
+    float scale = g_loss[b] / ((float)S * 2.f * sqrtf(closest_d[o] + 1e-10f));
+    float g9[9];
+    tri_grad(fc, p, scale, g9);
+    const int32_t* fi = faces + ((size_t)b * Fmax + f) * 3;
+    float* gp = grad_pos + (size_t)b * V * 3;
+#pragma unroll
+    for (int v = 0; v < 3; ++v)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (g9[v * 3 + k] != 0.f) atomicAdd(gp + (size_t)fi[v] * 3 + k, g9[v * 3 + k]);
+}
+
+__global__ void sqrt_mean_kernel(const float* __restrict__ d, int S, float eps, double* __restrict__ acc) {
+    int b = blockIdx.y;
+    double s = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) s += (double)sqrtf(d[(size_t)b * S + i] + eps);
+    s = warp_sum(s);
+    __shared__ double sw[8];
+    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sw[w];
+        atomicAdd(acc + b, t);
+    }
+}
+__global__ void sqrt_mean_finalize_kernel(const double* __restrict__ acc, const int32_t* __restrict__ counts, int S, int B, float* __restrict__ out) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    out[b] = (counts && counts[b] == 0) ? 1.0f : (float)(acc[b] / (double)S);      // empty surface -> 1 (deftet.py:162-166)
+}
+
+}  // namespace dtb
+
+using namespace dtb;
+
+constexpr int PFD_ALWAYS_CAP = 256;
+
+extern "C" int dtb_point_face_distance_grid_res(int Fmax) {
+    int g = (int)ceil(sqrt((double)(Fmax > 1 ? Fmax : 1)) * 0.5);
+    g = (g + 3) / 4 * 4;
+    if (g < 4) g = 4;
+    if (g > 128) g = 128;
+    return g;
+}
+extern "C" size_t dtb_point_face_distance_workspace(int B, int S, int Fmax, int G) {
+    (void)S;
+    if (G <= 0) G = dtb_point_face_distance_grid_res(Fmax);
+    G = (G + 3) / 4 * 4;
+    return pointgrid_workspace_bytes(B, Fmax, G, true, true) + align_up((size_t)B * PFD_ALWAYS_CAP * 4, 256) + 1024;
+}
+
+// counts (B,) i32: number of valid faces of each sample (the reference passes it as float n_face_b).
+extern "C" int dtb_point_face_distance_forward(const float* points, const float* faces, const int32_t* counts, int B, int S, int Fmax,
+                                               int G, float* closest_d, float* closest_f, void* workspace, size_t workspace_bytes,
+                                               void* stream) {
+    DTB_REQUIRE(points && counts && closest_d && closest_f, "point_face_distance_forward: null argument");
+    DTB_REQUIRE(B > 0 && S >= 0 && Fmax >= 0, "point_face_distance_forward: bad sizes");
+    if (S == 0) return DTB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (G <= 0) G = dtb_point_face_distance_grid_res(Fmax);
+    G = (G + 3) / 4 * 4;
+    Workspace ws(workspace, workspace_bytes);
+    PointGrid pg;
+    pointgrid_carve(pg, B, Fmax, G, true, true, ws);
+    int32_t* always = ws.take<int32_t>((size_t)B * PFD_ALWAYS_CAP);
+    unsigned* rmax = ws.take<unsigned>(B);
+    int32_t* n_always = ws.take<int32_t>(B);
+    if (!ws.ok || !workspace) { set_error("point_face_distance: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return DTB_EWORKSPACE; }
+    DTB_CUDA(cudaMemsetAsync(rmax, 0, B * sizeof(unsigned), st));
+    DTB_CUDA(cudaMemsetAsync(n_always, 0, B * sizeof(int32_t), st));
+    if (Fmax > 0) {
+        int rc = pointgrid_build_ragged(pg, faces, true, counts, st);
+        if (rc) return rc;
+        dim3 gs(cdiv(Fmax, 256), B);
+        face_stats_kernel<<<gs, 256, 0, st>>>(faces, counts, Fmax, rmax, always, n_always, PFD_ALWAYS_CAP);
+        DTB_LAUNCH_CHECK("face_stats");
+    }
+    dim3 grid(cdiv(S, 128), B);
+    pfd_forward_kernel<<<grid, 128, 0, st>>>(points, S, faces, counts, Fmax, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask,
+                                             rmax, always, n_always, PFD_ALWAYS_CAP, closest_d, closest_f);
+    DTB_LAUNCH_CHECK("pfd_forward");
+    return DTB_OK;
+}
+
+extern "C" int dtb_point_face_distance_backward(const float* points, const float* faces, const float* closest_f, const float* dl_dd, int B,
+                                                int S, int Fmax, float* dldface, void* stream) {
+    DTB_REQUIRE(points && closest_f && dl_dd && dldface, "point_face_distance_backward: null argument");
+    if (B == 0 || S == 0 || Fmax == 0) return DTB_OK;
+    dim3 grid(cdiv(S, 256), B);
+    pfd_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, S, faces, Fmax, closest_f, dl_dd, dldface);
+    DTB_LAUNCH_CHECK("pfd_backward");
+    return DTB_OK;
+}
+
+extern "C" int dtb_point_face_distance_backward_indexed(const float* points, const float* soup, const int32_t* faces, const float* closest_f,
+                                                        const float* closest_d, const float* g_loss, int B, int S, int Fmax, int V,
+                                                        float* grad_pos, void* stream) {
+    DTB_REQUIRE(points && soup && faces && closest_f && closest_d && g_loss && grad_pos, "point_face_distance_backward_indexed: null argument");
+    if (B == 0 || S == 0 || Fmax == 0) return DTB_OK;
+    dim3 grid(cdiv(S, 256), B);
+    pfd_backward_indexed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, S, soup, faces, Fmax, V, closest_f, closest_d, g_loss, grad_pos);
+    DTB_LAUNCH_CHECK("pfd_backward_indexed");
+    return DTB_OK;
+}
+
+// out[b] = mean_i sqrt(d[b,i] + eps)   (counts may be NULL; counts[b]==0 -> 1)
+extern "C" int dtb_sqrt_mean(const float* d, const int32_t* counts, int B, int S, float eps, double* acc, float* out, void* stream) {
+    DTB_REQUIRE(d && acc && out, "sqrt_mean: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    DTB_CUDA(cudaMemsetAsync(acc, 0, B * sizeof(double), st));
+    if (S > 0) {
+        dim3 grid(min(cdiv(S, 256), 128), B);
+        sqrt_mean_kernel<<<grid, 256, 0, st>>>(d, S, eps, acc);
+        DTB_LAUNCH_CHECK("sqrt_mean");
+    }
+    sqrt_mean_finalize_kernel<<<cdiv(B, 64), 64, 0, st>>>(acc, counts, S, B, out);
+    DTB_LAUNCH_CHECK("sqrt_mean_finalize");
+    return DTB_OK;
+}

@@ -95,6 +95,73 @@ size_t dtb_nearest_neighbor_workspace(int B, int Q, int M, int G);
 int dtb_nearest_neighbor(const float* queries, const float* points, int32_t* result, int B, int Q, int M, int G,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+int dtb_nearest_neighbor_ragged(const float* queries, const int32_t* q_counts, int q_mult, const float* points,
+                                int32_t* result, int B, int Qmax, int M, int G, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
+/* ---- A9 / A3: predicted-surface stage in a padded-ragged batch layout -----------------------------------
+ * The reference handles the ragged per-sample boundary sets with Python lists and a per-sample loop
+ * (layers/DefTet/deftet.py:89-103).  Here: faces (B,Fmax,3) i32 + counts (B,) i32, no host sync.
+ * dtb_boundary_faces = DefTet.get_boundary_index (deftet.py:186-195): interior faces face_fx3 (F,3) with their
+ * two tets face_tet_fx2 (F,2); a face is on the predicted surface of sample b when occ[b,t0]+occ[b,t1] == 1; it
+ * is emitted in table order, winding reversed when occ[b,t0] == 1.  *overflow is set to 1 if a sample has
+ * more than Fmax such faces (extra faces are dropped).
+ * dtb_surface_sample = mesh_utils.sample_surf_point_batch (utils/mesh_utils.py:290-299) with caller-provided
+ * u = sqrt(rand), v = rand of shape (B,Fmax,S): q (B,Fmax*S,3).
+ * dtb_chamfer_forward/backward = mesh_utils.point_point_distance + mean (utils/mesh_utils.py:360-366,
+ * deftet.py:177,180): loss[b] = mean_i sqrt(|q_i - gt[nn_i]|^2 + 1e-10) over the counts[b]*S samples (1 when
+ * the surface is empty, deftet.py:162-166); backward scatters through the sampling weights into grad_pos. */
+size_t dtb_boundary_faces_workspace(int B, int F);
+int dtb_boundary_faces(const int32_t* face_fx3, const int32_t* face_tet_fx2, const float* occ, int B, int T, int F, int Fmax,
+                       int32_t* out_faces, int32_t* out_counts, int32_t* overflow, void* workspace, size_t workspace_bytes,
+                       void* stream);
+int dtb_surface_sample(const float* pos, const int32_t* faces, const int32_t* counts, const float* u, const float* v, int B,
+                       int V, int Fmax, int S, float* q, void* stream);
+int dtb_chamfer_forward(const float* q, const int32_t* nn, const float* gt, const int32_t* counts, int B, int Fmax, int S,
+                        int M, double* acc, float* loss, void* stream);
+int dtb_chamfer_backward(const float* q, const int32_t* nn, const float* gt, const int32_t* faces, const int32_t* counts,
+                         const float* u, const float* v, const float* g_loss, int B, int V, int Fmax, int S, int M,
+                         float* grad_pos, void* stream);
+int dtb_face_soup(const float* pos, const int32_t* faces, const int32_t* counts, int B, int V, int Fmax, float* soup,
+                  void* stream);
+
+/* ---- A4: point -> triangle-set squared distance ------------------------------------------------------------
+ * Replaces tet_analytic_distance_batch.forward(points, faces, closest_f, closest_d, n_face_b) and
+ * .backward(points, faces, closest_f, dl_dclosest_d, dldtet) (layers/DefTet/tet_analytic_distance_batch/
+ * tet_analytic_distance.cpp:29-78; kernels tet_analytic_distance_for.cu:257-307, _back.cu:592-686).
+ * points (B,S,3), faces (B,Fmax,3,3) f32, counts (B,) i32 (the reference's float n_face_b), closest_d /
+ * closest_f (B,S) f32 (face id as float, -1 when no face is visible).  backward ACCUMULATES into dldface
+ * (B,Fmax,3,3) (caller zero-fills, like utils.py:65).  _backward_indexed is the engine form: chains
+ * loss_b = mean_i sqrt(d_i + 1e-10) (utils/mesh_utils.py:368-374) and scatters to grad_pos through the face
+ * vertex ids.  dtb_sqrt_mean: out[b] = mean_i sqrt(d[b,i] + eps) (1 when counts[b] == 0). */
+int dtb_point_face_distance_grid_res(int Fmax);
+size_t dtb_point_face_distance_workspace(int B, int S, int Fmax, int G);
+int dtb_point_face_distance_forward(const float* points, const float* faces, const int32_t* counts, int B, int S, int Fmax,
+                                    int G, float* closest_d, float* closest_f, void* workspace, size_t workspace_bytes,
+                                    void* stream);
+int dtb_point_face_distance_backward(const float* points, const float* faces, const float* closest_f, const float* dl_dd,
+                                     int B, int S, int Fmax, float* dldface, void* stream);
+int dtb_point_face_distance_backward_indexed(const float* points, const float* soup, const int32_t* faces,
+                                             const float* closest_f, const float* closest_d, const float* g_loss, int B,
+                                             int S, int Fmax, int V, float* grad_pos, void* stream);
+int dtb_sqrt_mean(const float* d, const int32_t* counts, int B, int S, float eps, double* acc, float* out, void* stream);
+
+/* ---- A5: boundary-face edge adjacency + normal-consistency loss -----------------------------------------------
+ * Replaces tet_face_adj_m_idx.forward(face_fx3x3, adj_idx[F,30]) (layers/DefTet/tet_face_adj_m_idx/
+ * tet_face_adj_m.cpp:26-34, kernel tet_face_adj_m_for.cu:72-108): per face the first 30 faces (ascending id)
+ * that share an edge, -1 padded.  soup != NULL groups vertices by coordinate value (what the reference
+ * does); soup == NULL groups by the vertex ids in faces (B,Fmax,3).  counts may be NULL.
+ * dtb_normal_loss_* = get_surface_normal_loss (utils/mesh_utils.py:16-39): mean over directed pairs of
+ * 1 - n_i.n_j, n = cross / sqrt(|cross|^2 + 1e-12) (:42-53); 0 when there is no pair, 1 when no face. */
+size_t dtb_face_adjacency_workspace(int B, int Fmax, int V);
+int dtb_face_adjacency(const float* soup, const int32_t* faces, const int32_t* counts, int B, int Fmax, int V, float* adj_f32,
+                       int32_t* adj_i32, int32_t* deg, void* workspace, size_t workspace_bytes, void* stream);
+int dtb_normal_loss_forward(const float* pos, const int32_t* faces, const int32_t* counts, const int32_t* adj, int B, int V,
+                            int Fmax, float* normals_ws, double* acc, float* loss, void* stream);
+int dtb_normal_loss_backward(const float* pos, const int32_t* faces, const int32_t* counts, const int32_t* adj,
+                             const float* normals_ws, const double* acc, const float* g_loss, int B, int V, int Fmax,
+                             float* gn_ws, float* grad_pos, void* stream);
+
 /* ---- device-wide primitives (exported for the self-tests; also usable by integrators) ----------------- */
 size_t dtb_prim_scan_workspace(size_t n);
 int dtb_prim_exclusive_scan_u32(const unsigned* in, unsigned* out, size_t n, unsigned* total, void* ws, size_t ws_bytes,

@@ -22,3 +22,19 @@ def rel_err(a, b, floor=0.0):
     b = torch.as_tensor(b).double().cpu()
     scale = max(float(b.abs().max()), floor, 1e-300)
     return float((a - b).abs().max()) / scale
+
+
+def sphere_occupancy(pos, tet, centres, radii):
+    """occ (B,T) float {0,1}: tet centroid inside the sample's sphere (analytic stand-in for kal check_sign)."""
+    B = pos.shape[0]
+    cen = pos[:, tet.long().reshape(-1)].reshape(B, -1, 4, 3).mean(dim=2)
+    c = torch.as_tensor(centres, dtype=pos.dtype).reshape(B, 1, 3)
+    r = torch.as_tensor(radii, dtype=pos.dtype).reshape(B, 1)
+    return ((cen - c).norm(dim=-1) < r).float()
+
+
+def sphere_points(B, n, centres, radii, seed=0):
+    gen = torch.Generator().manual_seed(seed)
+    d = torch.randn(B, n, 3, generator=gen)
+    d = d / d.norm(dim=-1, keepdim=True)
+    return d * torch.as_tensor(radii).reshape(B, 1, 1) + torch.as_tensor(centres, dtype=torch.float32).reshape(B, 1, 3)

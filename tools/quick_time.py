@@ -28,6 +28,20 @@ def timeit(fn, iters=10, warm=3, flush=None):
     return float(np.median(ts)), float(np.min(ts))
 
 
+def numpy_face_table(tets, n_vert):
+    """interior faces + their two tets (any order) -- dev helper until the GPU builder lands"""
+    loc = np.array([[0, 1, 2], [1, 0, 3], [2, 3, 0], [3, 2, 1]])
+    tri = tets[:, loc]                                   # T,4,3
+    srt = np.sort(tri, axis=-1).reshape(-1, 3)
+    key = (srt[:, 0] * n_vert + srt[:, 2]) * n_vert + srt[:, 1]
+    order = np.argsort(key, kind="stable")
+    ks = key[order]
+    same = ks[1:] == ks[:-1]
+    first = order[:-1][same]
+    second = order[1:][same]
+    return tri.reshape(-1, 3)[first].astype(np.int64), np.stack([first // 4, second // 4], 1).astype(np.int64)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--res", type=int, default=70)
@@ -72,8 +86,7 @@ def main():
                      ("nearest_neighbor", nn)]:
         med, mn = timeit(fn, a.iters, flush=flush)
         print("%-24s median %.3f ms  min %.3f ms  -> %.1f k tets/ms" % (name, med, mn, B * T / med / 1e3))
-    c, w = search.point_in_tet(pos, tet32, pts)
-    print("inside fraction", float((c >= 0).float().mean()))
+XX, float((c >= 0).float().mean()))
 
 
 if __name__ == "__main__":
