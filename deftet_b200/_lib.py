@@ -57,6 +57,12 @@ _EXTRA_SIGS = []
 def register_signatures(fn):
     """Other modules of the package append their own prototypes before first use."""
     _EXTRA_SIGS.append((fn.__name__, fn))
+    if _lib is not None:            # library already loaded: declare right away
+        def sig(name, restype, *argtypes):
+            f = getattr(_lib, name)
+            f.restype = restype
+            f.argtypes = list(argtypes)
+        fn(_lib, sig)
     return fn
 
 

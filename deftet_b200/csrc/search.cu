@@ -282,6 +282,7 @@ static int point_in_tet_impl(Src src, const float* points, int B, int T, int P, 
 
 extern "C" int dtb_point_in_tet(const float* pos, const int32_t* tet, const float* points, int B, int V, int T, int P, int G,
                                 float* cond, float* bary, void* workspace, size_t workspace_bytes, void* stream) {
+    if (P == 0) return DTB_OK;
     DTB_REQUIRE(pos && tet && points, "point_in_tet: null argument");
     PitIndexed src{pos, tet, V, T};
     return point_in_tet_impl(src, points, B, T, P, G, cond, bary, workspace, workspace_bytes, (cudaStream_t)stream);
@@ -289,6 +290,7 @@ extern "C" int dtb_point_in_tet(const float* pos, const int32_t* tet, const floa
 
 extern "C" int dtb_point_in_tet_soup(const float* tet_bxfx4x3, const float* points, int B, int T, int P, int G, float* cond,
                                      float* bary, void* workspace, size_t workspace_bytes, void* stream) {
+    if (P == 0) return DTB_OK;
     DTB_REQUIRE(tet_bxfx4x3 && points, "point_in_tet_soup: null argument");
     PitSoup src{tet_bxfx4x3, T};
     return point_in_tet_impl(src, points, B, T, P, G, cond, bary, workspace, workspace_bytes, (cudaStream_t)stream);

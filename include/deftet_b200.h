@@ -162,6 +162,46 @@ int dtb_normal_loss_backward(const float* pos, const int32_t* faces, const int32
                              const float* normals_ws, const double* acc, const float* g_loss, int B, int V, int Fmax,
                              float* gn_ws, float* grad_pos, void* stream);
 
+/* ---- A10-A14: topology builders ------------------------------------------------------------------------------
+ * Device-pointer forms (tet (T,4) i32 on the device; outputs sized by the caller for the worst case; counts
+ * are written to device int32 scalars, no host sync):
+ *   dtb_tet_point_adj    unique directed vertex pairs of utils/lib/tet_point_adj/run.cpp:20-56, sorted by (a,b)
+ *                        (the reference order is libstdc++ hash order); optional weight[e] = 1/deg(a), the
+ *                        values of the row-normalised matrix built at tet_point_adj/interface.py:42-54.
+ *   dtb_tet_to_face      utils/tet_utils.py:208-256 tet_to_face: interior faces in first-occurrence order with
+ *                        the winding of the first tet (local faces (0,1,2),(1,0,3),(2,3,0),(3,2,1)), their two
+ *                        tets and local face slots, and the faces seen once (cube boundary) in first-occurrence
+ *                        order.  counts[0] = interior, counts[1] = boundary.  Output pointers may be NULL.
+ *   dtb_tet_adj_share    utils/lib/tet_adj_share/run.cpp:40-97: rows (t0,t1,f0),(t1,t0,f1) in ascending
+ *                        face-key order; *n_out = number of shared faces (= rows / 2).
+ *   dtb_tet_face_adj     utils/lib/tet_face_adj/run.cpp:18-92: ordered pairs of tet-faces (4t+i) sharing an
+ *                        edge, grouped by the WRAPPED int32 edge key a*n+b in signed order (the reference
+ *                        overflows for n_point > 46340 and that is part of its output); *n_pairs may exceed
+ *                        `capacity`, in which case pairs is truncated.
+ *   dtb_collapse_vertices utils/lib/colaps_v/run.cpp:18-59: map_array[i] = id (first-occurrence order) of the
+ *                        point's "%.5f-%.5f-%.5f" key (so -0.00000 != 0.00000), inverse_idx[id] = first index.
+ * Host-pointer forms dtb_host_*: the exact argument lists of the reference's `extern "C" void run(...)`; they
+ * allocate, copy, run and synchronise themselves, and return an error code instead of void. */
+size_t dtb_tet_point_adj_workspace(int n_point, int T);
+int dtb_tet_point_adj(const int32_t* tet, int n_point, int T, int32_t* edges, float* weight, int32_t* n_edge, void* workspace,
+                      size_t workspace_bytes, void* stream);
+size_t dtb_tet_to_face_workspace(int T);
+int dtb_tet_to_face(const int32_t* tet, int n_point, int T, int32_t* face_fx3, int32_t* face_tet_fx2, int32_t* face_slot_fx2,
+                    int32_t* boundary_fx3, int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+size_t dtb_tet_adj_share_workspace(int T);
+int dtb_tet_adj_share(const int32_t* tet, int n_point, int T, int32_t* out, int32_t* n_out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+size_t dtb_tet_face_adj_workspace(int T);
+int dtb_tet_face_adj(const int32_t* tet, int n_point, int T, int32_t* pairs, long long capacity, int32_t* n_pairs,
+                     void* workspace, size_t workspace_bytes, void* stream);
+size_t dtb_collapse_vertices_workspace(int N);
+int dtb_collapse_vertices(const float* points, int N, int32_t* map_array, int32_t* inverse_idx, int32_t* n_unique,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int dtb_host_tet_point_adj(const int32_t* tet_list, int32_t* edge_p, int32_t* n_edge, int n_point, int n_tet);
+int dtb_host_tet_adj_share(const int32_t* tet_list, int32_t* face_edge_p, int32_t* n_face_edge_p, int n_point, int n_tet);
+int dtb_host_tet_face_adj(const int32_t* tet_list, int32_t* face_edge_p, int32_t* n_face_edge_p, int n_point, int n_tet);
+int dtb_host_colaps_v(const float* point_p, int32_t* map_array_p, int32_t* inverse_idx_p, int32_t* n_colaps_v_p, int n_point);
+
 /* ---- device-wide primitives (exported for the self-tests; also usable by integrators) ----------------- */
 size_t dtb_prim_scan_workspace(size_t n);
 int dtb_prim_exclusive_scan_u32(const unsigned* in, unsigned* out, size_t n, unsigned* total, void* ws, size_t ws_bytes,

@@ -102,33 +102,42 @@ def face_adjacency(face_fx3x3, n_max_nei=30, threads=None):
 
 
 # ---- the reference's own builders, compiled from /root/reference into oracle/_ref (kind: "reference") ----
+# They are executed out of process through oracle/ref_driver (see the note at the top of ref_driver.c).
+import subprocess
+import tempfile
+
+
 def ref_lib(name):
+    """Path of oracle/_ref/<name>/run.so, or None when it has not been built."""
     path = os.path.join(HERE, "_ref", name, "run.so")
-    if not os.path.exists(path):
-        return None
-    return C.CDLL(path)
+    drv = os.path.join(HERE, "ref_driver")
+    return path if (os.path.exists(path) and os.path.exists(drv)) else None
+
+
+def _drive(mode, name, payload, out_ints):
+    path = ref_lib(name)
+    if path is None:
+        raise RuntimeError("oracle/_ref/%s/run.so or oracle/ref_driver missing (needs /root/reference at build time)" % name)
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        with open(fin, "wb") as f:
+            f.write(payload)
+        subprocess.run([os.path.join(HERE, "ref_driver"), mode, path, fin, fout], check=True)
+        return np.fromfile(fout, dtype=np.int32, count=out_ints)
 
 
 def ref_run_tet_builder(name, tet_tx4, n_point, out_rows, out_cols):
     """Call `run(int* tet, int* out, int* n_out, int n_point, int n_tet)` of utils/lib/<name>/run.cpp."""
-    L = ref_lib(name)
-    if L is None:
-        raise RuntimeError("oracle/_ref/%s/run.so missing (needs /root/reference at build time)" % name)
     tet = np.ascontiguousarray(tet_tx4, dtype=np.int32)
-    out = np.zeros((out_rows, out_cols), dtype=np.int32)
-    n = np.zeros(1, dtype=np.int32)
-    L.run(_p(tet), _p(out), _p(n), C.c_int(int(n_point)), C.c_int(tet.shape[0]))
-    return out, int(n[0])
+    cap = int(out_rows) * int(out_cols)
+    hdr = np.array([n_point, tet.shape[0], cap], dtype=np.int32)
+    res = _drive("tet", name, hdr.tobytes() + tet.tobytes(), 1 + cap)
+    return res[1:].reshape(out_rows, out_cols), int(res[0])
 
 
 def ref_colaps_v(points_nx3):
-    L = ref_lib("colaps_v")
-    if L is None:
-        raise RuntimeError("oracle/_ref/colaps_v/run.so missing")
     pts = _f32(points_nx3)
     n = pts.shape[0]
-    m = np.zeros(n, dtype=np.int32)
-    inv = np.zeros(n, dtype=np.int32)
-    cnt = np.zeros(1, dtype=np.int32)
-    L.run(_p(pts), _p(m), _p(inv), _p(cnt), C.c_int(n))
-    return m, inv[:cnt[0]]
+    res = _drive("colaps", "colaps_v", np.array([n], dtype=np.int32).tobytes() + pts.tobytes(), 1 + 2 * n)
+    cnt = int(res[0])
+    return res[1:1 + n].copy(), res[1 + n:1 + n + cnt].copy()

@@ -86,7 +86,42 @@ def main():
                      ("nearest_neighbor", nn)]:
         med, mn = timeit(fn, a.iters, flush=flush)
         print("%-24s median %.3f ms  min %.3f ms  -> %.1f k tets/ms" % (name, med, mn, B * T / med / 1e3))
-XX, float((c >= 0).float().mean()))
+    c, w = search.point_in_tet(pos, tet32, pts)
+    print("inside fraction", float((c >= 0).float().mean()))
+
+    # ---- surface stage ----
+    from deftet_b200 import surface
+    from tests.util import sphere_occupancy
+    t0 = time.time()
+    f3, ft2 = numpy_face_table(g.tets, V)
+    print("numpy face table %.2fs, F_s=%d" % (time.time() - t0, f3.shape[0]))
+    occ = sphere_occupancy(pos.cpu(), tet, [[0, 0, 0]] * B, [0.3] * B).to(dev)
+    table = surface.FaceTable(torch.from_numpy(f3).to(dev), torch.from_numpy(ft2).to(dev))
+    Fmax = 16384
+    faces, counts, ovf = surface.boundary_faces(table, occ, Fmax)
+    print("boundary counts", counts.tolist(), "overflow", int(ovf.item()))
+    S = 20
+    u = torch.sqrt(torch.rand(B, Fmax, S, device=dev))
+    v = torch.rand(B, Fmax, S, device=dev)
+
+    def bf():
+        return surface.boundary_faces(table, occ, Fmax)
+
+    def ch_fb():
+        l = surface.surface_chamfer(p, faces, counts, u, v, surf)
+        l.sum().backward()
+
+    def sd_fb():
+        l = surface.surface_distance(p, faces, counts, surf)
+        l.sum().backward()
+
+    def nl_fb():
+        l = surface.surface_normal_loss(p, faces, counts)
+        l.sum().backward()
+
+    for name, fn in [("boundary_faces", bf), ("chamfer fwd+bwd", ch_fb), ("surface_distance fwd+bwd", sd_fb), ("normal_loss fwd+bwd", nl_fb)]:
+        med, mn = timeit(fn, a.iters, flush=flush)
+        print("%-24s median %.3f ms  min %.3f ms  -> %.1f k tets/ms" % (name, med, mn, B * T / med / 1e3))
 
 
 if __name__ == "__main__":
