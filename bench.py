@@ -1,0 +1,459 @@
+#!/usr/bin/env python
+"""bench.py -- tets/ms of one forward+backward pass of the DefTet geometry hot path (BASELINE.json metric).
+
+Workload (configs[2] of BASELINE.json): res-70 tetrahedral grid, batch 8 per GPU, full
+surface-align + chamfer + AMIPS loss and the point-in-tet occupancy query with its barycentric backward:
+  per-tet energies A6-A8 fwd+bwd, point-in-tet A1 (100k query points / sample) + barycentric backward,
+  boundary extraction A9, one-sided chamfer A2/A3 (20 samples per boundary face vs 100k GT points),
+  point->surface distance A4 fwd+bwd, normal consistency A5 fwd+bwd; gradient w.r.t. batch-shared vertex
+  offsets (V,3), all-reduced (SUM) across ranks when N > 1 (weak scaling: batch 8 per GPU).
+  value = n_gpus * B * T / t_step[ms].
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          this engine (CUDA, sm_100a)
+  python bench.py --impl reference ...                        the reference's algorithms on the host cores
+                                                              (oracle port: the reference has no CPU path for
+                                                              its CUDA-only kernels)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+
+# ------------------------------------------------------------------------------------------------- scene
+def analytic_scene(grid, B, P, S, seed, device):
+    """Synthetic stand-in for one ShapeNet batch: per-sample vertex deformation, GT shape = sphere,
+    occupancy labels by the analytic inside test on tet centroids, GT surface points, SDF query points."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.from_numpy(grid.centred())
+    mask = torch.from_numpy(grid.mask.astype(np.float32))
+    res = grid.res
+    deform = (torch.rand(B, grid.n_vert, 3, generator=g) * 2 - 1) * (0.25 / res) * mask
+    pos = base.unsqueeze(0) + deform
+    centres = (torch.rand(B, 1, 3, generator=g) - 0.5) * 0.1
+    radii = 0.2 + 0.15 * torch.rand(B, 1, generator=g)
+    tet = torch.from_numpy(grid.tets)
+    cen = pos[:, tet.reshape(-1)].reshape(B, -1, 4, 3).mean(dim=2)
+    occ = ((cen - centres).norm(dim=-1) < radii).float()
+    d = torch.randn(B, S, 3, generator=g)
+    gt = d / d.norm(dim=-1, keepdim=True) * radii.unsqueeze(-1) + centres
+    pts = (torch.rand(B, P, 3, generator=g) - 0.5) * 1.05                       # dataloader.py:108
+    target = ((pts - centres).norm(dim=-1) < radii).float()
+    vfield = ((pos - centres).norm(dim=-1) < radii).float()                      # per-vertex occupancy to interpolate
+    out = dict(pos=pos, occ=occ, gt=gt, pts=pts, target=target, vfield=vfield)
+    return {k: v.float().contiguous().to(device) for k, v in out.items()}
+
+
+class Step:
+    """One forward+backward of the geometry losses; gradient lands in delta.grad (V,3)."""
+
+    WEIGHTS = dict(amips=1.0, edge=1.0, volume_variance=1e6, chamfer=1.0, distance=1.0, normal=0.1, occupancy=1.0)
+
+    def __init__(self, engine, samples, Fmax, S_face):
+        self.eng = engine
+        self.Fmax, self.S_face = Fmax, S_face
+        self.delta = torch.zeros(engine.n_vert, 3, device=engine.device, requires_grad=True)
+        self.samples = samples
+
+    def forward_backward(self, sc, u, v):
+        eng = self.eng
+        pos = sc["pos"] + self.delta.unsqueeze(0)
+        out = eng.losses(pos, sc["occ"], sc["gt"], u, v, sc["pts"])
+        cond, bary = out["condition"], out["barycentric"]
+        tid = cond.squeeze(-1).clamp(min=0).long()
+        vid = eng.tet.long()[tid]                                                   # (B,P,4)
+        phi = torch.gather(sc["vfield"], 1, vid.reshape(vid.shape[0], -1)).reshape(vid.shape)
+        pred = (bary * phi).sum(dim=-1)
+        inside = (cond.squeeze(-1) >= 0).float()
+        occ_loss = (((pred - sc["target"]) ** 2) * inside).sum(dim=-1) / inside.sum(dim=-1).clamp(min=1.0)
+        w = self.WEIGHTS
+        per_sample = (w["amips"] * out["amips"] + w["edge"] * out["edge"] + w["volume_variance"] * out["volume_variance"]
+                      + w["chamfer"] * out["chamfer"] + w["distance"] * out["distance"] + w["normal"] * out["normal"]
+                      + w["occupancy"] * occ_loss)
+        loss = per_sample.sum()
+        loss.backward()
+        return loss.detach(), out["boundary_counts"], out["boundary_overflow"]
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- cpu leg
+def cpu_reference_step(grid, B, P, S, seed, budget_s=20.0, threads=None):
+    """The reference's algorithms on the host (oracle port), on a bounded sample of the workload, scaled to a
+    full step.  Returns (tets_per_ms, cores, description)."""
+    from oracle import energies as orc_e
+    from oracle import native as orc
+    from oracle import surface as orc_s
+    from oracle import builders as orc_b
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sc = analytic_scene(grid, B, P, S, seed, "cpu")
+    tet = torch.from_numpy(grid.tets)
+    T = grid.n_tet
+    t_total, parts = 0.0, {}
+    # A6-A8 fwd+bwd: the reference's own pure-PyTorch path, full batch
+    inv = orc_e.tet_inverse_v(torch.from_numpy(grid.centred()), tet)
+    t0 = time.perf_counter()
+    orc_e.energies_with_grad(sc["pos"], tet, inv, (1.0, 1.0, 1e6))
+    parts["energies_full"] = time.perf_counter() - t0
+    t_total += parts["energies_full"]
+    soup = orc_e.gather_tets(sc["pos"][:1], tet).numpy()
+    # A1 brute force on n1 points of sample 0, scaled to B*P
+    n1 = max(threads * 8, 256)
+    t0 = time.perf_counter()
+    orc.point_in_tet(soup, sc["pts"][:1, :n1].numpy(), threads)
+    dt = time.perf_counter() - t0
+    parts["point_in_tet_%dpts" % n1] = dt
+    t_total += dt * (B * P / n1)
+    # boundary of sample 0 (numpy face table) for A2/A4/A5
+    from tools.quick_time import numpy_face_table
+    f3, ft2 = numpy_face_table(grid.tets, grid.n_vert)
+    bnd = orc_s.get_boundary_index(torch.from_numpy(f3), torch.from_numpy(ft2), sc["occ"][:1])[0]
+    Fb = int(bnd.shape[0])
+    faces = orc_s.gather_faces(sc["pos"][:1], bnd)
+    # A2: n2 queries vs S points, scaled to B * 20 * Fb
+    n2 = max(threads * 64, 2048)
+    q = sc["gt"][:1, :n2] + 0.01
+    t0 = time.perf_counter()
+    orc.nearest_neighbor(q.numpy(), sc["gt"][:1].numpy(), threads)
+    dt = time.perf_counter() - t0
+    parts["nn_%dq" % n2] = dt
+    t_total += dt * (B * 20 * Fb / n2)
+    # A4 forward: n4 points vs Fb faces, scaled to B*S (backward is O(S), negligible)
+    n4 = max(threads * 16, 512)
+    t0 = time.perf_counter()
+    orc.point_face_distance(sc["gt"][:1, :n4].numpy(), faces.numpy(), None, threads)
+    dt = time.perf_counter() - t0
+    parts["face_dist_%dpts" % n4] = dt
+    t_total += dt * (B * S / n4)
+    # A5: full O(Fb^2) for one sample, times B
+    t0 = time.perf_counter()
+    orc.face_adjacency(faces[0].numpy(), 30, threads)
+    dt = time.perf_counter() - t0
+    parts["face_adj_1sample"] = dt
+    t_total += dt * B
+    desc = "oracle port on %d threads; bounded sample scaled to one full step (B=%d,T=%d,P=%d,S=%d,F_b=%d): %s" % (
+        threads, B, T, P, S, Fb, ", ".join("%s=%.3fs" % kv for kv in parts.items()))
+    return B * T / (t_total * 1e3), threads, desc
+
+
+# ------------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--res", type=int, default=70)
+    ap.add_argument("--batch", type=int, default=8, help="samples per GPU (weak scaling)")
+    ap.add_argument("--points", type=int, default=100000)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from deftet_b200.grid import acute_lattice_grid
+    grid = acute_lattice_grid(args.res)
+    B, P, S, T, V = args.batch, args.points, args.points, grid.n_tet, grid.n_vert
+    config = {"workload": "res=%d batch %d/GPU, full surf+chamfer+AMIPS loss + point-in-tet (BASELINE.json configs[2])" % (args.res, B),
+              "grid": "synthetic acute lattice V=%d T=%d" % (V, T), "global_batch": B * max(world, 1), "query_points": P,
+              "gt_points": S, "parallelism": "dp%d" % max(world, 1)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vals = []
+        for k in range(max(1, min(args.steps, 3))):
+            v, cores, desc = cpu_reference_step(grid, B, P, S, 1000 * 3 + k)
+            vals.append(v)
+        v = float(np.median(vals))
+        line = {"impl": "reference", "metric": "tets/ms fwd+bwd (occ+AMIPS+chamfer) res-%d" % args.res, "value": v, "unit": "tets/ms",
+                "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": B * T / v, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "tets/ms", "cores": cores, "kind": "port", "sample": desc},
+                "e2e": {"value": v, "unit": "tets/ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (deftet_b200 has no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from deftet_b200.engine import GeometryEngine
+    Fmax, S_face = 16384, 20
+    eng = GeometryEngine(grid.centred(), grid.tets, max_boundary_faces=Fmax, samples_per_face=S_face, device=dev)
+    NSETS = 4          # inputs rotate over NSETS sets (> L2 together) so that no step finds its inputs in L2
+    scenes = [analytic_scene(grid, B, P, S, 1000 * 3 + 17 * rank + s, dev) for s in range(NSETS)]
+    gen = torch.Generator(device=dev).manual_seed(7 + rank)
+    uv = [(torch.sqrt(torch.rand(B, Fmax, S_face, device=dev, generator=gen)), torch.rand(B, Fmax, S_face, device=dev, generator=gen))
+          for _ in range(NSETS)]
+    set_bytes = sum(t.numel() * 4 for t in scenes[0].values()) + 2 * B * Fmax * S_face * 4
+    config["l2"] = "inputs rotate over %d sets of %.0f MB (> 126 MB L2 in total)" % (NSETS, set_bytes / 1e6)
+    step = Step(eng, scenes, Fmax, S_face)
+
+    def run_eager(s):
+        step.delta.grad = None
+        return step.forward_backward(scenes[s], *uv[s])
+
+    # warm-up (also JIT/allocator warm-up) on a side stream as graph capture requires
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for w in range(max(3, args.warmup)):
+            loss, counts, ovf = run_eager(w % NSETS)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    assert int(ovf.item()) == 0, "boundary face capacity exceeded"
+    graphs = None
+    if not args.no_graph:
+        try:
+            graphs = []
+            for s in range(NSETS):
+                g = torch.cuda.CUDAGraph()
+                step.delta.grad = None
+                with torch.cuda.graph(g):
+                    l, _, _ = step.forward_backward(scenes[s], *uv[s])
+                graphs.append((g, l, step.delta.grad))
+            torch.cuda.synchronize()
+        except Exception as e:  # pragma: no cover
+            graphs = None
+            config["graph"] = "capture failed: %s" % str(e)[:80]
+            torch.cuda.synchronize()
+
+    def run(s):
+        if graphs is not None:
+            g, l, grad = graphs[s % NSETS]
+            g.replay()
+        else:
+            l, _, _ = run_eager(s % NSETS)
+            grad = step.delta.grad
+        if world > 1:
+            dist.all_reduce(grad)          # the one collective of the step: SUM of the shared-offset gradient
+        return l, grad
+
+    for w in range(args.warmup):
+        run(w)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        l, grad = run(k)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = float(ms.item()) / args.steps
+    value = world * B * T / ms_per_step
+
+    # ---- e2e: host buffers in, losses + gradient out, through the same public call ------------------------
+    host = [{k: v.cpu().pin_memory() for k, v in sc.items()} for sc in scenes]
+    stat = scenes[0]
+    h2d = sum(v.numel() * 4 for v in host[0].values())
+    out_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    out_grad = torch.empty(V, 3, dtype=torch.float32).pin_memory()
+    d2h = out_loss.numel() * 4 + out_grad.numel() * 4
+
+    def run_e2e(k):
+        for name, t in host[k % NSETS].items():
+            stat[name].copy_(t, non_blocking=True)
+        if graphs is not None:
+            g, l, grad = graphs[0]
+            g.replay()
+        else:
+            l, _, _ = run_eager(0)
+            grad = step.delta.grad
+        if world > 1:
+            dist.all_reduce(grad)
+        out_loss.copy_(l, non_blocking=True)
+        out_grad.copy_(grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for w in range(3):
+        run_e2e(w)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        run_e2e(k)
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * T / (float(e2e_ms.item()) / args.steps)
+
+    # ---- per-kernel-group timing (eager, CUDA events) for the roofline of the dominant group -------------
+    roof, launches = None, None
+    if rank == 0:
+        roof, launches = roofline_pass(eng, step, scenes, uv, B, T, V, P, S, Fmax, S_face, NSETS)
+        cpu = None
+        if not args.skip_cpu:
+            try:
+                v, cores, desc = cpu_reference_step(grid, B, P, S, 1000 * 3)
+                cpu = {"value": v, "unit": "tets/ms", "cores": cores, "kind": "port", "sample": desc}
+            except Exception as e:  # pragma: no cover
+                cpu = {"value": None, "unit": "tets/ms", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %s" % str(e)[:120]}
+        config["graph"] = config.get("graph", "cuda graph replay" if graphs is not None else "eager")
+        line = {"metric": "tets/ms fwd+bwd (occ+AMIPS+chamfer) res-%d" % args.res, "value": value, "unit": "tets/ms", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "tets/ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "loss": float(l.item())}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def roofline_pass(eng, step, scenes, uv, B, T, V, P, S, Fmax, S_face, NSETS, iters=12):
+    """Eager pass with CUDA events around each kernel group; roofline of the dominant one.
+    Algorithmic bytes per launch."""
+    from deftet_b200 import energies, search, surface
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    sc0 = scenes[0]
+    pos = (sc0["pos"] + step.delta.detach().unsqueeze(0)).requires_grad_(True)
+    faces, counts, _ = surface.boundary_faces(eng.face_table, sc0["occ"], Fmax)
+    Fb = float(counts.float().mean().item())
+    Fs = eng.face_table.n_face
+    groups = {}
+
+    def timed(name, fn, bytes_alg):
+        for _ in range(2):
+            fn()
+        evs = []
+        for k in range(iters):
+            sc = scenes[k % NSETS]
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(sc, uv[k % NSETS]) if fn.__code__.co_argcount == 2 else fn(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        groups[name] = (ms, bytes_alg)
+
+    def g_energy(sc, uvk):
+        p = (sc["pos"]).requires_grad_(True)
+        am, ed, vv = energies.tet_energies(p, eng.tet, eng.inverse_v)
+        (am + ed + vv).sum().backward()
+
+    def g_pit(sc, uvk):
+        p = (sc["pos"]).requires_grad_(True)
+        c, w = search.point_in_tet(p, eng.tet, sc["pts"])
+        (w * w).sum().backward()
+
+    def g_bf(sc, uvk):
+        surface.boundary_faces(eng.face_table, sc["occ"], Fmax)
+
+    def g_ch(sc, uvk):
+        p = (sc["pos"]).requires_grad_(True)
+        surface.surface_chamfer(p, faces, counts, uvk[0], uvk[1], sc["gt"]).sum().backward()
+
+    def g_sd(sc, uvk):
+        p = (sc["pos"]).requires_grad_(True)
+        surface.surface_distance(p, faces, counts, sc["gt"]).sum().backward()
+
+    def g_nl(sc, uvk):
+        p = (sc["pos"]).requires_grad_(True)
+        surface.surface_normal_loss(p, faces, counts).sum().backward()
+
+    Q = 20 * Fb
+    timed("energies A6-A8 fwd+bwd", g_energy, 2 * (16 * T + 36 * T + 12 * B * V) + 12 * B * V + 8 * B * T)
+    timed("point_in_tet A1 fwd+bwd", g_pit, B * (12 * P + 4 * P + 16 * P) + 12 * B * V + 16 * T + B * (16 * P + 12 * P) + 12 * B * V)
+    timed("boundary_faces A9", g_bf, 4 * B * T + 20 * Fs + 12 * B * Fb)
+    timed("chamfer A2/A3 fwd+bwd", g_ch, B * (12 * Q + 12 * S + 4 * Q) + 12 * B * V)
+    timed("surface_distance A4 fwd+bwd", g_sd, 2 * B * (12 * S + 36 * Fb + 8 * S))
+    timed("normal_loss A5 fwd+bwd", g_nl, B * (2 * 36 * Fb + 4 * 6 * Fb))
+    name, (ms, by) = max(groups.items(), key=lambda kv: kv[1][0])
+    achieved = by / (ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes": by, "ms": ms,
+            "groups_ms": {k: round(v[0], 4) for k, v in groups.items()},
+            "groups_frac": {k: round(v[1] / (v[0] * 1e-3) / 1e9 / peak, 4) for k, v in groups.items()}}
+    launches = count_launches(step, scenes, uv)
+    return roof, launches
+
+
+def count_launches(step, scenes, uv):
+    """Number of deftet_b200 kernels launched by one eager step (CUPTI via torch.profiler; static fallback)."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        step.delta.grad = None
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step.forward_backward(scenes[0], *uv[0])
+            torch.cuda.synchronize()
+        n = sum(1 for e in prof.events() if "dtb::" in e.name)
+        if n > 0:
+            return n
+    except Exception:
+        pass
+    return 75       # static count of the eager step
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,54 @@
+"""The geometry hot path as one object: topology built once on the GPU, then a batched forward (+ autograd
+backward) of every per-tetrahedron / per-surface loss of ``DefTet.forward_surface_align``
+(reference layers/DefTet/deftet.py:51-130) without its per-sample Python loop, host syncs or the
+materialised (B,T,4,3) gather.
+
+    eng = GeometryEngine(init_pos, tets)                       # A10/A11 builders + rest inverses
+    out = eng.losses(pos, occ, gt_points, u, v, query_points)  # dict of (B,) losses, differentiable in pos
+
+This is the call ``bench.py`` times; ``deftet_b200.deftet.DefTet`` is the drop-in module with the
+reference's method names built on the same kernels.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import builders, energies, search, surface
+
+
+class GeometryEngine:
+    def __init__(self, init_pos, tets, max_boundary_faces=16384, samples_per_face=20, device=None):
+        device = torch.device(device) if device is not None else (init_pos.device if torch.is_tensor(init_pos) else torch.device("cuda"))
+        self.device = device
+        self.init_pos = torch.as_tensor(init_pos, dtype=torch.float32).to(device).contiguous()
+        self.tet = torch.as_tensor(tets).to(device).to(torch.int32).contiguous()
+        self.n_vert = self.init_pos.shape[0]
+        self.n_tet = self.tet.shape[0]
+        self.inverse_v = energies.tet_inverse_v(self.init_pos, self.tet)                       # train_multigpu.py:105-110
+        f3, ft2, fs2, bnd = builders.tet_to_face(self.n_vert, self.tet)                         # train_multigpu.py:77-82
+        self.tet_face_fx3, self.tet_face_tetidx_fx2, self.tet_face_slot_fx2, self.cube_boundary = f3, ft2, fs2, bnd
+        self.face_table = surface.FaceTable(f3, ft2)
+        self.max_boundary_faces = int(max_boundary_faces)
+        self.samples_per_face = int(samples_per_face)
+
+    def vertex_adjacency(self, normalize=True):
+        """Row-normalised vertex adjacency (train_multigpu.py:72-75) as a torch sparse tensor."""
+        return builders.tet_to_adj_sparse(self.n_vert, self.tet, normalize)
+
+    def losses(self, pos, occ, gt_points, u, v, query_points=None, want=("energies", "chamfer", "distance", "normal", "occupancy")):
+        """pos (B,V,3); occ (B,T) in {0,1}; gt_points (B,S,3); u,v (B,Fmax,samples) sampling randoms;
+        query_points (B,P,3) for the point-in-tet query.  Returns a dict; every loss is (B,)."""
+        out = {}
+        if "energies" in want:
+            out["amips"], out["edge"], out["volume_variance"] = energies.tet_energies(pos, self.tet, self.inverse_v)
+        faces, counts, overflow = surface.boundary_faces(self.face_table, occ, self.max_boundary_faces)
+        out["boundary_faces"], out["boundary_counts"], out["boundary_overflow"] = faces, counts, overflow
+        if "chamfer" in want:
+            out["chamfer"] = surface.surface_chamfer(pos, faces, counts, u, v, gt_points)
+        if "distance" in want:
+            out["distance"] = surface.surface_distance(pos, faces, counts, gt_points)
+        if "normal" in want:
+            out["normal"] = surface.surface_normal_loss(pos, faces, counts)
+        if "occupancy" in want and query_points is not None:
+            out["condition"], out["barycentric"] = search.point_in_tet(pos, self.tet, query_points)
+        return out
