@@ -32,13 +32,19 @@ __global__ void __launch_bounds__(256) pg_bbox_kernel(const float* __restrict__ 
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) { mn[k] = warp_min(mn[k]); mx[k] = warp_max(mx[k]); }
+    __shared__ float s_mn[8][3], s_mx[8][3];
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (mn[k] <= mx[k]) {
-                atomicMin(&bbox_ord[(size_t)b * 6 + k], f2ord(mn[k]));
-                atomicMax(&bbox_ord[(size_t)b * 6 + 3 + k], f2ord(mx[k]));
-            }
+        for (int k = 0; k < 3; ++k) { s_mn[threadIdx.x >> 5][k] = mn[k]; s_mx[threadIdx.x >> 5][k] = mx[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        int k = threadIdx.x;
+        float a = s_mn[0][k], c = s_mx[0][k];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a = fminf(a, s_mn[w][k]); c = fmaxf(c, s_mx[w][k]); }
+        if (a <= c) {
+            atomicMin(&bbox_ord[(size_t)b * 6 + k], f2ord(a));
+            atomicMax(&bbox_ord[(size_t)b * 6 + 3 + k], f2ord(c));
         }
     }
 }
@@ -144,7 +150,7 @@ int pointgrid_build_ragged(PointGrid& pg, const float* items, bool tri, const in
     DTB_LAUNCH_CHECK("pg_init");
     DTB_CUDA(cudaMemsetAsync(pg.cell_start, 0, cells * sizeof(unsigned), st));
     if (N > 0) {
-        dim3 gb(min(cdiv(N, 256 * 4), 256), B);
+        dim3 gb(min(cdiv(N, 256 * 8), 64), B);
         pg_bbox_kernel<<<gb, 256, 0, st>>>(items, tri, N, counts, pg.bbox_ord);
         DTB_LAUNCH_CHECK("pg_bbox");
     }

@@ -234,6 +234,54 @@ __global__ void __launch_bounds__(128) nn_query_kernel(const float* __restrict__
     result[(size_t)b * Q + i] = v.bi;
 }
 
+
+// ---- interpolation of a per-vertex field at the query points through the barycentric weights ----------
+// out[b,p,:] = sum_k w[b,p,k] * field[b, tet[cond[b,p]][k], :]   (zeros where cond < 0)
+__global__ void __launch_bounds__(256) interp_fwd_kernel(const float* __restrict__ field, const int32_t* __restrict__ tet, int V, int C,
+                                                         const float* __restrict__ cond, const float* __restrict__ bary, int P,
+                                                         float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    size_t o = (size_t)b * P + i;
+    float c = cond[o];
+    float* y = out + o * C;
+    if (!(c >= 0.f)) { for (int k = 0; k < C; ++k) y[k] = 0.f; return; }
+    int4 id = reinterpret_cast<const int4*>(tet)[(int)c];
+    float4 w = reinterpret_cast<const float4*>(bary)[o];
+    const float* fb = field + (size_t)b * V * C;
+    for (int k = 0; k < C; ++k)
+        y[k] = w.x * fb[(size_t)id.x * C + k] + w.y * fb[(size_t)id.y * C + k] + w.z * fb[(size_t)id.z * C + k] + w.w * fb[(size_t)id.w * C + k];
+}
+__global__ void __launch_bounds__(256) interp_bwd_kernel(const float* __restrict__ field, const int32_t* __restrict__ tet, int V, int C,
+                                                         const float* __restrict__ cond, const float* __restrict__ bary, int P,
+                                                         const float* __restrict__ g_out, float* __restrict__ g_field,
+                                                         float* __restrict__ g_bary) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    size_t o = (size_t)b * P + i;
+    float c = cond[o];
+    float4 gw = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c >= 0.f) {
+        int4 id = reinterpret_cast<const int4*>(tet)[(int)c];
+        float4 w = reinterpret_cast<const float4*>(bary)[o];
+        const float* fb = field + (size_t)b * V * C;
+        const float* g = g_out + o * C;
+        for (int k = 0; k < C; ++k) {
+            float gk = g[k];
+            gw.x += gk * fb[(size_t)id.x * C + k]; gw.y += gk * fb[(size_t)id.y * C + k];
+            gw.z += gk * fb[(size_t)id.z * C + k]; gw.w += gk * fb[(size_t)id.w * C + k];
+            if (g_field) {
+                float* gf = g_field + (size_t)b * V * C;
+                atomicAdd(gf + (size_t)id.x * C + k, gk * w.x); atomicAdd(gf + (size_t)id.y * C + k, gk * w.y);
+                atomicAdd(gf + (size_t)id.z * C + k, gk * w.z); atomicAdd(gf + (size_t)id.w * C + k, gk * w.w);
+            }
+        }
+    }
+    if (g_bary) reinterpret_cast<float4*>(g_bary)[o] = gw;
+}
+
 }  // namespace dtb
 
 using namespace dtb;
@@ -358,4 +406,25 @@ extern "C" int dtb_nearest_neighbor_ragged(const float* queries, const int32_t* 
                                            void* stream) {
     DTB_REQUIRE(q_counts != nullptr, "nearest_neighbor_ragged: null q_counts");
     return nearest_neighbor_impl(queries, points, result, B, Qmax, M, G, q_counts, q_mult, workspace, workspace_bytes, stream);
+}
+
+// field (B,V,C), out (B,P,C): interpolate a per-vertex field at the query points (see kernel comment)
+extern "C" int dtb_tet_interpolate_forward(const float* field, const int32_t* tet, const float* cond, const float* bary, int B, int V, int C,
+                                           int P, float* out, void* stream) {
+    if (P == 0 || B == 0) return DTB_OK;
+    DTB_REQUIRE(field && tet && cond && bary && out && C > 0, "tet_interpolate_forward: bad argument");
+    dim3 grid(cdiv(P, 256), B);
+    interp_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(field, tet, V, C, cond, bary, P, out);
+    DTB_LAUNCH_CHECK("interp_fwd");
+    return DTB_OK;
+}
+// g_field (B,V,C) is ACCUMULATED (may be NULL); g_bary (B,P,4) is overwritten (may be NULL)
+extern "C" int dtb_tet_interpolate_backward(const float* field, const int32_t* tet, const float* cond, const float* bary, const float* g_out,
+                                            int B, int V, int C, int P, float* g_field, float* g_bary, void* stream) {
+    if (P == 0 || B == 0) return DTB_OK;
+    DTB_REQUIRE(field && tet && cond && bary && g_out && C > 0, "tet_interpolate_backward: bad argument");
+    dim3 grid(cdiv(P, 256), B);
+    interp_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(field, tet, V, C, cond, bary, P, g_out, g_field, g_bary);
+    DTB_LAUNCH_CHECK("interp_bwd");
+    return DTB_OK;
 }

@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(256) face_stats_kernel(const float* __restrict
 struct TriVisitor {
     const float* soup;      // this sample's (Fmax,3,3)
     float p[3];
+    float rmax;             // largest centroid-to-vertex distance of the sample (inflated)
     float best; int bi;
     __device__ __forceinline__ float bound() const { return best; }
     __device__ __forceinline__ void face(int f) {
@@ -130,37 +131,152 @@ struct TriVisitor {
         float d = tri_distance(a, b, c, p, FWD_MAX_DIS, h);
         if (best > d || (d == best && bi >= 0 && f < bi)) { best = d; bi = f; }
     }
-    __device__ __forceinline__ void item(const float4& it) { face(__float_as_int(it.w)); }
+    __device__ __forceinline__ void item(const float4& it) {
+        // cheap conservative reject: the face lies inside the ball (centroid, rmax)
+        float dx = it.x - p[0], dy = it.y - p[1], dz = it.z - p[2];
+        float lb = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz) - rmax, 0.f) * 0.9999f;
+        if (lb * lb > best) return;
+        face(__float_as_int(it.w));
+    }
 };
 
-__global__ void __launch_bounds__(128) pfd_forward_kernel(const float* __restrict__ points, int S, const float* __restrict__ soup,
-                                                          const int32_t* __restrict__ counts, int Fmax, int G,
-                                                          const unsigned* __restrict__ bbox_ord, const unsigned* __restrict__ cell_start,
-                                                          const unsigned* __restrict__ cell_end, const float4* __restrict__ sorted,
-                                                          const unsigned long long* __restrict__ mask,
-                                                          const unsigned* __restrict__ rmax_bits, const int32_t* __restrict__ always,
-                                                          const int32_t* __restrict__ n_always, int always_cap,
-                                                          float* __restrict__ closest_d, float* __restrict__ closest_f) {
+// ---- query binning: the S points of each sample counting-sorted by the brick of the FACE grid they fall in ----
+__global__ void __launch_bounds__(256) qbin_count_kernel(const float* __restrict__ points, int S, int G, const unsigned* __restrict__ bbox_ord,
+                                                         unsigned* __restrict__ qcount, unsigned* __restrict__ qbrick) {
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S) return;
-    const float* pp = points + ((size_t)b * S + i) * 3;
-    TriVisitor v;
-    v.soup = soup + (size_t)b * Fmax * 9;
-    v.p[0] = pp[0]; v.p[1] = pp[1]; v.p[2] = pp[2];
-    v.best = 10000.0f; v.bi = -1;              // tet_analytic_distance_for.cu:278-279
+    GridParams g = grid_params(bbox_ord, b, G);
+    const float* p = points + ((size_t)b * S + i) * 3;
+    const int NB = G >> 2;
+    int bx = cell_coord(p[0], g.ox, g.inv_h, G) >> 2, by = cell_coord(p[1], g.oy, g.inv_h, G) >> 2, bz = cell_coord(p[2], g.oz, g.inv_h, G) >> 2;
+    unsigned id = (unsigned)b * NB * NB * NB + ((unsigned)bz * NB + by) * NB + bx;
+    qbrick[(size_t)b * S + i] = id;
+    atomicAdd(qcount + id, 1u);
+}
+__global__ void __launch_bounds__(256) qbin_fill_kernel(const float* __restrict__ points, int S, const unsigned* __restrict__ qbrick,
+                                                        unsigned* __restrict__ qend, float4* __restrict__ qsorted) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const float* p = points + ((size_t)b * S + i) * 3;
+    unsigned dst = atomicAdd(qend + qbrick[(size_t)b * S + i], 1u);
+    qsorted[dst] = make_float4(p[0], p[1], p[2], __int_as_float(i));
+}
+
+// One CTA per brick of queries: the faces binned in the 3x3x3 surrounding bricks are staged once in shared
+// memory (centroid + 9 coordinates) and every query of the brick filters / evaluates them from there.  A query
+// whose best distance cannot be certified against faces outside that neighbourhood falls back to the
+// general brick walk.  Results are identical to the brute-force scan (lexicographic minimum).
+constexpr int PFD_THREADS = 128;
+constexpr int PFD_CHUNK = 256;      // candidate faces staged per round
+
+__global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
+    int S, const float* __restrict__ soup, const int32_t* __restrict__ counts, int Fmax, int G, const unsigned* __restrict__ bbox_ord,
+    const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end, const float4* __restrict__ sorted,
+    const unsigned long long* __restrict__ mask, const unsigned* __restrict__ rmax_bits, const int32_t* __restrict__ always,
+    const int32_t* __restrict__ n_always, int always_cap, const unsigned* __restrict__ qstart, const unsigned* __restrict__ qend,
+    const float4* __restrict__ qsorted, float* __restrict__ closest_d, float* __restrict__ closest_f) {
+    __shared__ float4 s_cen[PFD_CHUNK];
+    __shared__ float s_tri[PFD_CHUNK * 9];
+    __shared__ unsigned s_rs[27], s_re[27];
+    __shared__ unsigned s_total;
+    const int b = blockIdx.y;
+    const int NB = G >> 2;
+    const int brick = blockIdx.x;                       // brick of this sample
+    const size_t qb = (size_t)b * NB * NB * NB + brick;
+    const unsigned q0 = qstart[qb], q1 = qend[qb];
+    if (q0 == q1) return;
     const int nf = counts[b];
     const int na = n_always[b];
-    if (na > always_cap) {                     // too many unreliable faces: exact brute force for this sample
-        for (int f = 0; f < nf; ++f) v.face(f);
-    } else if (nf > 0) {
-        for (int k = 0; k < na; ++k) v.face(always[(size_t)b * always_cap + k]);
-        GridParams g = grid_params(bbox_ord, b, G);
-        float rmax = __uint_as_float(rmax_bits[b]);
-        brick_walk(v.p[0], v.p[1], v.p[2], g, G, rmax * 1.001f, cell_start, cell_end, sorted, mask, (size_t)b * G * G * G, v);
+    const int bz0 = brick / (NB * NB), by0 = (brick / NB) % NB, bx0 = brick % NB;
+    const size_t cell_base = (size_t)b * G * G * G;
+    const float* sb = soup + (size_t)b * Fmax * 9;
+    const GridParams g = grid_params(bbox_ord, b, G);
+    const float rmax = __uint_as_float(rmax_bits[b]) * 1.001f + 1e-7f;
+    const bool brute = na > always_cap;
+    // candidate ranges of the 27 neighbouring bricks (a brick's items are contiguous in `sorted`)
+    if (threadIdx.x < 27) {
+        int dz = threadIdx.x / 9 - 1, dy = (threadIdx.x / 3) % 3 - 1, dx = threadIdx.x % 3 - 1;
+        int z = bz0 + dz, y = by0 + dy, x = bx0 + dx;
+        unsigned rs = 0, re = 0;
+        if (!brute && nf > 0 && z >= 0 && z < NB && y >= 0 && y < NB && x >= 0 && x < NB) {
+            size_t br = ((size_t)z * NB + y) * NB + x;
+            if (mask[(cell_base >> 6) + br]) { rs = cell_start[cell_base + br * 64]; re = cell_end[cell_base + br * 64 + 63]; }
+        }
+        s_rs[threadIdx.x] = rs; s_re[threadIdx.x] = re;
     }
-    closest_d[(size_t)b * S + i] = v.best;
-    closest_f[(size_t)b * S + i] = (float)v.bi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int k = 0; k < 27; ++k) t += s_re[k] - s_rs[k];
+        s_total = t;
+    }
+    __syncthreads();
+    const unsigned total = s_total;
+    const float bw = 4.0f * g.h;
+    const float slack = 1e-3f * g.h + 1e-6f * (fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz) + (float)G * g.h);
+    for (unsigned qbase = q0; qbase < q1; qbase += PFD_THREADS) {
+        const unsigned qi = qbase + threadIdx.x;
+        const bool active = qi < q1;
+        TriVisitor v;
+        v.soup = sb; v.rmax = rmax; v.best = 10000.0f; v.bi = -1;
+        int orig = 0;
+        if (active) {
+            float4 q = qsorted[qi];
+            v.p[0] = q.x; v.p[1] = q.y; v.p[2] = q.z;
+            orig = __float_as_int(q.w);
+            if (brute) { for (int f = 0; f < nf; ++f) v.face(f); }
+            else { for (int k = 0; k < na; ++k) v.face(always[(size_t)b * always_cap + k]); }
+        } else { v.p[0] = v.p[1] = v.p[2] = 0.f; }
+        // stage candidates chunk by chunk
+        for (unsigned c0 = 0; c0 < total; c0 += PFD_CHUNK) {
+            __syncthreads();
+            for (unsigned k = threadIdx.x; k < PFD_CHUNK && c0 + k < total; k += PFD_THREADS) {
+                unsigned off = c0 + k;
+                int r = 0;
+                while (off >= s_re[r] - s_rs[r]) { off -= s_re[r] - s_rs[r]; ++r; }
+                float4 it = sorted[s_rs[r] + off];
+                s_cen[k] = it;
+                const float* t = sb + (size_t)__float_as_int(it.w) * 9;
+#pragma unroll
+                for (int m = 0; m < 9; ++m) s_tri[k * 9 + m] = t[m];
+            }
+            __syncthreads();
+            if (active) {
+                const int n = (int)min((unsigned)PFD_CHUNK, total - c0);
+                for (int k = 0; k < n; ++k) {
+                    float4 it = s_cen[k];
+                    float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
+                    float lb = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz) - rmax, 0.f) * 0.9999f;
+                    if (lb * lb > v.best) continue;
+                    const float* t = s_tri + k * 9;
+                    float a[3] = {t[0], t[1], t[2]}, bb[3] = {t[3], t[4], t[5]}, c[3] = {t[6], t[7], t[8]};
+                    TriHit h;
+                    float d = tri_distance(a, bb, c, v.p, FWD_MAX_DIS, h);
+                    int f = __float_as_int(it.w);
+                    if (v.best > d || (d == v.best && v.bi >= 0 && f < v.bi)) { v.best = d; v.bi = f; }
+                }
+            }
+        }
+        if (active && !brute && nf > 0) {
+            // certify against faces outside the 3x3x3 neighbourhood: their centroids are at least db away
+            float db = 3.0e38f;
+            if (bx0 >= 2) db = fminf(db, v.p[0] - (g.ox + (float)(bx0 - 1) * bw));
+            if (bx0 + 2 <= NB - 1) db = fminf(db, (g.ox + (float)(bx0 + 2) * bw) - v.p[0]);
+            if (by0 >= 2) db = fminf(db, v.p[1] - (g.oy + (float)(by0 - 1) * bw));
+            if (by0 + 2 <= NB - 1) db = fminf(db, (g.oy + (float)(by0 + 2) * bw) - v.p[1]);
+            if (bz0 >= 2) db = fminf(db, v.p[2] - (g.oz + (float)(bz0 - 1) * bw));
+            if (bz0 + 2 <= NB - 1) db = fminf(db, (g.oz + (float)(bz0 + 2) * bw) - v.p[2]);
+            float lb = fmaxf(db - rmax - slack, 0.f) * 0.9999f;
+            if (!(lb * lb > v.best))
+                brick_walk(v.p[0], v.p[1], v.p[2], g, G, rmax, cell_start, cell_end, sorted, mask, cell_base, v);
+        }
+        if (active) {
+            closest_d[(size_t)b * S + orig] = v.best;
+            closest_f[(size_t)b * S + orig] = (float)v.bi;
+        }
+    }
 }
 
 // ---- backward ---------------------------------------------------------------------------------------
@@ -273,6 +389,11 @@ using namespace dtb;
 
 constexpr int PFD_ALWAYS_CAP = 256;
 
+__global__ void pfd_fill_none_kernel(float* __restrict__ d, float* __restrict__ f, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { d[i] = 10000.0f; f[i] = -1.0f; }
+}
+
 extern "C" int dtb_point_face_distance_grid_res(int Fmax) {
     int g = (int)ceil(sqrt((double)(Fmax > 1 ? Fmax : 1)) * 0.5);
     g = (g + 3) / 4 * 4;
@@ -281,10 +402,11 @@ extern "C" int dtb_point_face_distance_grid_res(int Fmax) {
     return g;
 }
 extern "C" size_t dtb_point_face_distance_workspace(int B, int S, int Fmax, int G) {
-    (void)S;
     if (G <= 0) G = dtb_point_face_distance_grid_res(Fmax);
     G = (G + 3) / 4 * 4;
-    return pointgrid_workspace_bytes(B, Fmax, G, true, true) + align_up((size_t)B * PFD_ALWAYS_CAP * 4, 256) + 1024;
+    size_t nbr = (size_t)B * (G / 4) * (G / 4) * (G / 4);
+    return pointgrid_workspace_bytes(B, Fmax, G, true, true) + align_up((size_t)B * PFD_ALWAYS_CAP * 4, 256) + 1024 +
+           2 * align_up(nbr * 4, 256) + align_up((size_t)B * S * 4, 256) + align_up((size_t)B * S * 16, 256) + scan_workspace_bytes(nbr) + 256;
 }
 
 // counts (B,) i32: number of valid faces of each sample (the reference passes it as float n_face_b).
@@ -295,6 +417,11 @@ extern "C" int dtb_point_face_distance_forward(const float* points, const float*
     DTB_REQUIRE(B > 0 && S >= 0 && Fmax >= 0, "point_face_distance_forward: bad sizes");
     if (S == 0) return DTB_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (Fmax == 0) {                       // no faces at all: min_d = 10000, min_idx = -1 (for.cu:278-279)
+        pfd_fill_none_kernel<<<cdiv((long long)B * S, 256), 256, 0, st>>>(closest_d, closest_f, (size_t)B * S);
+        DTB_LAUNCH_CHECK("pfd_fill_none");
+        return DTB_OK;
+    }
     if (G <= 0) G = dtb_point_face_distance_grid_res(Fmax);
     G = (G + 3) / 4 * 4;
     Workspace ws(workspace, workspace_bytes);
@@ -303,20 +430,40 @@ extern "C" int dtb_point_face_distance_forward(const float* points, const float*
     int32_t* always = ws.take<int32_t>((size_t)B * PFD_ALWAYS_CAP);
     unsigned* rmax = ws.take<unsigned>(B);
     int32_t* n_always = ws.take<int32_t>(B);
+    const size_t nbr = (size_t)B * (G / 4) * (G / 4) * (G / 4);
+    unsigned* qstart = ws.take<unsigned>(nbr);
+    unsigned* qend = ws.take<unsigned>(nbr);
+    unsigned* qbrick = ws.take<unsigned>((size_t)B * S);
+    float4* qsorted = ws.take<float4>((size_t)B * S);
+    size_t qsb = scan_workspace_bytes(nbr);
+    void* qsws = ws.take<char>(qsb);
     if (!ws.ok || !workspace) { set_error("point_face_distance: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return DTB_EWORKSPACE; }
     DTB_CUDA(cudaMemsetAsync(rmax, 0, B * sizeof(unsigned), st));
     DTB_CUDA(cudaMemsetAsync(n_always, 0, B * sizeof(int32_t), st));
-    if (Fmax > 0) {
+    {
         int rc = pointgrid_build_ragged(pg, faces, true, counts, st);
         if (rc) return rc;
         dim3 gs(cdiv(Fmax, 256), B);
         face_stats_kernel<<<gs, 256, 0, st>>>(faces, counts, Fmax, rmax, always, n_always, PFD_ALWAYS_CAP);
         DTB_LAUNCH_CHECK("face_stats");
     }
-    dim3 grid(cdiv(S, 128), B);
-    pfd_forward_kernel<<<grid, 128, 0, st>>>(points, S, faces, counts, Fmax, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask,
-                                             rmax, always, n_always, PFD_ALWAYS_CAP, closest_d, closest_f);
-    DTB_LAUNCH_CHECK("pfd_forward");
+    {
+        dim3 gq(cdiv(S, 256), B);
+        DTB_CUDA(cudaMemsetAsync(qstart, 0, nbr * sizeof(unsigned), st));
+        qbin_count_kernel<<<gq, 256, 0, st>>>(points, S, G, pg.bbox_ord, qstart, qbrick);
+        DTB_LAUNCH_CHECK("qbin_count");
+        int rc = exclusive_scan_u32(qstart, qstart, nbr, nullptr, qsws, qsb, st);
+        if (rc) return rc;
+        DTB_CUDA(cudaMemcpyAsync(qend, qstart, nbr * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+        qbin_fill_kernel<<<gq, 256, 0, st>>>(points, S, qbrick, qend, qsorted);
+        DTB_LAUNCH_CHECK("qbin_fill");
+    }
+    const int NB = G / 4;
+    dim3 grid(NB * NB * NB, B);
+    pfd_forward_tiled_kernel<<<grid, PFD_THREADS, 0, st>>>(S, faces, counts, Fmax, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted,
+                                                           pg.mask, rmax, always, n_always, PFD_ALWAYS_CAP, qstart, qend, qsorted,
+                                                           closest_d, closest_f);
+    DTB_LAUNCH_CHECK("pfd_forward_tiled");
     return DTB_OK;
 }
 

@@ -22,6 +22,8 @@ def _search_sigs(lib, sig):
     sig("dtb_point_in_tet", i, vp, vp, vp, i, i, i, i, i, vp, vp, vp, sz, vp)
     sig("dtb_point_in_tet_soup", i, vp, vp, i, i, i, i, vp, vp, vp, sz, vp)
     sig("dtb_tet_barycentric_backward", i, vp, vp, vp, vp, vp, i, i, i, i, vp, vp, vp)
+    sig("dtb_tet_interpolate_forward", i, vp, vp, vp, vp, i, i, i, i, vp, vp)
+    sig("dtb_tet_interpolate_backward", i, vp, vp, vp, vp, vp, i, i, i, i, vp, vp, vp)
     sig("dtb_nearest_neighbor_grid_res", i, i)
     sig("dtb_nearest_neighbor_workspace", sz, i, i, i, i)
     sig("dtb_nearest_neighbor", i, vp, vp, vp, i, i, i, i, vp, sz, vp)
@@ -98,6 +100,47 @@ def point_in_tet(pos, tet, points, grid_res=0):
     if tet.dtype != torch.int32:
         tet = tet.to(torch.int32)
     return _PointInTet.apply(pos, tet.contiguous(), points, int(grid_res))
+
+
+class _TetInterpolate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, field, tet32, cond, bary):
+        field, bary = _f32c(field), _f32c(bary)
+        B, V, Cn = field.shape
+        P = cond.shape[1]
+        out = torch.empty(B, P, Cn, device=field.device)
+        with torch.cuda.device(field.device):
+            _lib.check(_lib.lib().dtb_tet_interpolate_forward(_lib.ptr(field), _lib.ptr(tet32), _lib.ptr(cond), _lib.ptr(bary), B, V, Cn, P,
+                                                              _lib.ptr(out), _lib.stream_ptr()), "dtb_tet_interpolate_forward")
+        ctx.save_for_backward(field, tet32, cond, bary)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        field, tet32, cond, bary = ctx.saved_tensors
+        B, V, Cn = field.shape
+        P = cond.shape[1]
+        g_out = _f32c(g_out)
+        g_field = torch.zeros_like(field) if ctx.needs_input_grad[0] else None
+        g_bary = torch.empty_like(bary) if ctx.needs_input_grad[3] else None
+        with torch.cuda.device(field.device):
+            _lib.check(_lib.lib().dtb_tet_interpolate_backward(_lib.ptr(field), _lib.ptr(tet32), _lib.ptr(cond), _lib.ptr(bary),
+                                                               _lib.ptr(g_out), B, V, Cn, P, _lib.ptr(g_field), _lib.ptr(g_bary),
+                                                               _lib.stream_ptr()), "dtb_tet_interpolate_backward")
+        return g_field, None, None, g_bary
+
+
+def tet_interpolate(field_bxvxc, tet, cond, bary):
+    """Interpolate a per-vertex field at the query points located by ``point_in_tet``: -> (B,P,C)."""
+    if tet.dtype != torch.int32:
+        tet = tet.to(torch.int32)
+    return _TetInterpolate.apply(field_bxvxc, tet.contiguous(), cond.contiguous(), bary)
+
+
+def paste_occ(pred_tet_occ, condition):
+    """``DefTet.paste_occ`` (deftet.py:132-136), including its in-place clamp of misses (-1) to tet 0."""
+    condition[condition < 0] = 0
+    return torch.gather(input=pred_tet_occ, index=condition.long().squeeze(-1), dim=1)
 
 
 # --------------------------------------------------------------------------------------------------- A2

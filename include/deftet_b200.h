@@ -86,6 +86,14 @@ int dtb_tet_barycentric_backward(const float* pos, const int32_t* tet, const flo
                                  const float* g_w, int B, int V, int T, int P, float* grad_pos, float* grad_points,
                                  void* stream);
 
+/* Interpolation of a per-vertex field (B,V,C) at the query points through the weights of dtb_point_in_tet
+ * (the differentiable form of DefTet.paste_occ, layers/DefTet/deftet.py:132-136): out (B,P,C), zeros where
+ * cond == -1.  backward ACCUMULATES into g_field (may be NULL) and overwrites g_bary (B,P,4) (may be NULL). */
+int dtb_tet_interpolate_forward(const float* field, const int32_t* tet, const float* cond, const float* bary, int B, int V, int C,
+                                int P, float* out, void* stream);
+int dtb_tet_interpolate_backward(const float* field, const int32_t* tet, const float* cond, const float* bary,
+                                 const float* g_out, int B, int V, int C, int P, float* g_field, float* g_bary, void* stream);
+
 /* ---- A2: 1-nearest-neighbour index (one-sided chamfer) -----------------------------------------------
  * Replaces nearest_neighbor_cuda.forward(queries, points, result_int32, batch, nq, np, dim=3)
  * (layers/nearest_neighbor/nearest_neighbor.cpp:34-52, kernel nearest_neighbor_cuda.cu:17-55):

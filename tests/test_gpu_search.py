@@ -104,3 +104,35 @@ def test_nearest_neighbor_quantised_ties():
     ref = orc.nearest_neighbor(q.numpy(), pts.numpy())
     out = search.nearest_neighbor_index(q.cuda(), pts.cuda())
     assert np.array_equal(out.cpu().numpy().astype(np.int64), ref)
+
+
+def test_tet_interpolate_matches_torch_gather():
+    from deftet_b200 import search
+    res, B, P, C = 8, 2, 3000, 3
+    g, pos, tet = deformed_grid(res, B, seed=2)
+    pts = _query_points(B, P, 4)
+    gen = torch.Generator().manual_seed(0)
+    field = torch.randn(B, g.n_vert, C, generator=gen)
+    dpos = pos.cuda()
+    dfield = field.cuda().requires_grad_(True)
+    cond, bary = search.point_in_tet(dpos, tet.cuda(), pts.cuda())
+    bary = bary.detach().requires_grad_(True)
+    out = search.tet_interpolate(dfield, tet.cuda(), cond, bary)
+    gw = torch.randn(B, P, C, generator=gen)
+    (out * gw.cuda()).sum().backward()
+    # torch reference
+    rfield = field.clone().requires_grad_(True)
+    rb = bary.detach().cpu().clone().requires_grad_(True)
+    c = cond.cpu().squeeze(-1)
+    vid = tet.long()[c.clamp(min=0).long()]
+    phi = torch.gather(rfield.unsqueeze(2).expand(-1, -1, 4, -1), 1, vid.unsqueeze(-1).expand(-1, -1, -1, C))
+    ref = (rb.unsqueeze(-1) * phi).sum(dim=2) * (c >= 0).float().unsqueeze(-1)
+    (ref * gw).sum().backward()
+    assert rel_err(out, ref.detach()) < 1e-6
+    assert rel_err(dfield.grad, rfield.grad) < 1e-5
+    assert rel_err(bary.grad, rb.grad * (c >= 0).float().unsqueeze(-1)) < 1e-6
+    # paste_occ drop-in: misses are clamped to tet 0 in place
+    occ = torch.rand(B, g.n_tet, generator=gen).cuda()
+    cc = cond.clone()
+    pasted = search.paste_occ(occ, cc)
+    assert float(cc.min()) >= 0 and pasted.shape == (B, P)
