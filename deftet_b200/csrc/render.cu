@@ -1,0 +1,344 @@
+// A15: per-pixel tetrahedral-face volume rasterizer -- stand-in for kal.render.mesh.deftet_sparse_render, the
+// call at diff_render/diftet_6_subdiv/5_rendereq/deftetrneder.py:97-100 (Kaolin is third-party, un-vendored and
+// un-pinned in the reference: "parity unpinned"; the semantics below are the call-site contract + SURVEY.md 8c):
+//   for every pixel: all faces whose 2-D triangle contains the pixel (w1 = k1/(k3+eps), w2 = k2/(k3+eps),
+//   w0 = 1-w1-w2, reject if any w < 0) and whose interpolated z lies inside the pixel's [min, max] range; the
+//   first K such faces in ascending face id, sorted near-to-far (z descending: the camera looks down -z);
+//   output barycentrically interpolated features (B,P,K,d) and face ids (B,P,K) int64, void slots = 0 / -1.
+//   backward: gradients to face_features and face_vertices_image (not to z, not to the pixel).
+// B200 design: faces are binned into a 2-D grid over the pixels' bounding box ((cell, face) pairs, radix-sorted so
+// that every cell lists its faces in ascending id); one WARP per pixel streams its cell's list with coalesced
+// loads, appends hits in order with ballot/popc, bitonic-sorts them by depth in shared memory and writes the K
+// slots of the pixel with coalesced stores (the dense (B,P,K,d) output is the bandwidth hog: 4.6 GB per 800x800
+// view at K=300).
+#include "prims.cuh"
+#include "deftet_b200.h"
+
+namespace dtb {
+
+typedef unsigned long long u64;
+
+struct PixGrid { float ox, oy, inv; int R; };
+__device__ __forceinline__ PixGrid pix_grid(const unsigned* bbox_ord, int b, int R) {
+    const unsigned* q = bbox_ord + (size_t)b * 4;
+    float x0 = ord2f(q[0]), y0 = ord2f(q[1]), x1 = ord2f(q[2]), y1 = ord2f(q[3]);
+    float ext = fmaxf(fmaxf(x1 - x0, y1 - y0), 1e-20f) * (1.0f + 1e-6f);
+    PixGrid g; g.ox = x0; g.oy = y0; g.inv = (float)R / ext; g.R = R;
+    return g;
+}
+__device__ __forceinline__ int pix_cell(float x, float o, float inv, int R) {
+    float f = floorf((x - o) * inv);
+    f = fminf(fmaxf(f, 0.f), (float)(R - 1));
+    return (int)f;
+}
+
+__global__ void rd_init_kernel(unsigned* bbox_ord, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * 4) bbox_ord[i] = ((i % 4) < 2) ? 0xffffffffu : 0u;
+}
+__global__ void __launch_bounds__(256) rd_bbox_kernel(const float* __restrict__ pix, int P, unsigned* __restrict__ bbox_ord) {
+    int b = blockIdx.y;
+    float mn[2] = {3.4e38f, 3.4e38f}, mx[2] = {-3.4e38f, -3.4e38f};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+        float x = pix[((size_t)b * P + i) * 2], y = pix[((size_t)b * P + i) * 2 + 1];
+        mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x); mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { mn[k] = warp_min(mn[k]); mx[k] = warp_max(mx[k]); }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (mn[k] <= mx[k]) { atomicMin(&bbox_ord[(size_t)b * 4 + k], f2ord(mn[k])); atomicMax(&bbox_ord[(size_t)b * 4 + 2 + k], f2ord(mx[k])); }
+    }
+}
+
+// cells overlapped by a face's xy bounding box (clipped to the pixel grid); faces entirely outside are dropped
+__device__ __forceinline__ bool face_cells(const float* xy, const PixGrid& g, const unsigned* bbox_ord, int b, int& cx0, int& cx1, int& cy0, int& cy1) {
+    float x0 = fminf(xy[0], fminf(xy[2], xy[4])), x1 = fmaxf(xy[0], fmaxf(xy[2], xy[4]));
+    float y0 = fminf(xy[1], fminf(xy[3], xy[5])), y1 = fmaxf(xy[1], fmaxf(xy[3], xy[5]));
+    const unsigned* q = bbox_ord + (size_t)b * 4;
+    if (!(x1 >= ord2f(q[0]) && x0 <= ord2f(q[2]) && y1 >= ord2f(q[1]) && y0 <= ord2f(q[3]))) return false;
+    cx0 = pix_cell(x0, g.ox, g.inv, g.R); cx1 = pix_cell(x1, g.ox, g.inv, g.R);
+    cy0 = pix_cell(y0, g.oy, g.inv, g.R); cy1 = pix_cell(y1, g.oy, g.inv, g.R);
+    return true;
+}
+__global__ void __launch_bounds__(256) rd_count_kernel(const float* __restrict__ face_xy, int F, int R, const unsigned* __restrict__ bbox_ord,
+                                                       unsigned* __restrict__ npairs) {
+    int b = blockIdx.y;
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    PixGrid g = pix_grid(bbox_ord, b, R);
+    int cx0, cx1, cy0, cy1;
+    unsigned n = 0;
+    if (face_cells(face_xy + ((size_t)b * F + f) * 6, g, bbox_ord, b, cx0, cx1, cy0, cy1)) n = (unsigned)((cx1 - cx0 + 1) * (cy1 - cy0 + 1));
+    npairs[(size_t)b * F + f] = n;
+}
+__global__ void __launch_bounds__(256) rd_pairs_kernel(const float* __restrict__ face_xy, int F, int R, const unsigned* __restrict__ bbox_ord,
+                                                       const unsigned* __restrict__ pair_off, size_t cap, u64* __restrict__ keys,
+                                                       unsigned* __restrict__ vals, unsigned* __restrict__ cell_cnt) {
+    int b = blockIdx.y;
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    PixGrid g = pix_grid(bbox_ord, b, R);
+    int cx0, cx1, cy0, cy1;
+    if (!face_cells(face_xy + ((size_t)b * F + f) * 6, g, bbox_ord, b, cx0, cx1, cy0, cy1)) return;
+    size_t o = pair_off[(size_t)b * F + f];
+    for (int cy = cy0; cy <= cy1; ++cy)
+        for (int cx = cx0; cx <= cx1; ++cx) {
+            u64 cell = ((u64)b * R + cy) * R + cx;
+            if (o < cap) { keys[o] = cell * (u64)F + (u64)f; vals[o] = (unsigned)f; }
+            atomicAdd(cell_cnt + cell, 1u);
+            ++o;
+        }
+}
+// pad keys beyond the real pair count so that they sort to the end
+__global__ void rd_pad_kernel(u64* keys, unsigned* vals, const unsigned* total, size_t cap) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap && i >= *total) { keys[i] = ~0ull; vals[i] = 0xffffffffu; }
+}
+
+// cell_end[c] = cell_start[c+1] (the pair list is sorted by cell); flags overflow of the pair capacity
+__global__ void rd_cell_end_kernel(const unsigned* __restrict__ cstart, const unsigned* __restrict__ total, size_t cells, size_t cap,
+                                   unsigned* __restrict__ cend, int32_t* __restrict__ overflow) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells) return;
+    unsigned t = *total;
+    if (c == 0) *overflow = (t > cap) ? 1 : 0;
+    unsigned e = (c + 1 < cells) ? cstart[c + 1] : t;
+    unsigned lim = (unsigned)min((size_t)t, cap);
+    cend[c] = min(e, lim);
+}
+
+struct Bary2 { float w0, w1, w2, depth; bool hit; };
+__device__ __forceinline__ Bary2 face_test(const float* xy, const float* z, float px, float py, float zmin, float zmax, float eps) {
+    Bary2 r; r.hit = false;
+    float ax = xy[0], ay = xy[1], bx = xy[2], by = xy[3], cx = xy[4], cy = xy[5];
+    if (px < fminf(ax, fminf(bx, cx)) || px > fmaxf(ax, fmaxf(bx, cx)) || py < fminf(ay, fminf(by, cy)) || py > fmaxf(ay, fmaxf(by, cy))) return r;
+    // hit / miss and the depth order are decided with non-contracted fp32 (bit-identical to the CPU oracle)
+    float m = xsub(bx, ax), pp = xsub(by, ay), n = xsub(cx, ax), q = xsub(cy, ay), s = xsub(px, ax), t = xsub(py, ay);
+    float k1 = xsub(xmul(s, q), xmul(n, t)), k2 = xsub(xmul(m, t), xmul(s, pp)), k3 = xsub(xmul(m, q), xmul(n, pp));
+    float den = xadd(k3, eps);
+    r.w1 = xdiv(k1, den); r.w2 = xdiv(k2, den); r.w0 = xsub(xsub(1.f, r.w1), r.w2);
+    if (r.w0 < 0.f || r.w1 < 0.f || r.w2 < 0.f) return r;
+    r.depth = xadd(xadd(xmul(r.w0, z[0]), xmul(r.w1, z[1])), xmul(r.w2, z[2]));
+    if (!(r.depth >= zmin && r.depth <= zmax)) return r;
+    r.hit = true;
+    return r;
+}
+
+constexpr int RD_WARPS = 4;
+
+// one warp per pixel.  dynamic smem: RD_WARPS * Kpad * (depth f32, face i32, w1 f32, w2 f32)
+__global__ void __launch_bounds__(RD_WARPS * 32) rd_forward_kernel(
+    const float* __restrict__ pix, const float* __restrict__ ranges, const float* __restrict__ face_z, const float* __restrict__ face_xy,
+    const float* __restrict__ face_feat, int P, int F, int D, int K, int Kpad, float eps, int R, const unsigned* __restrict__ bbox_ord,
+    const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end, const unsigned* __restrict__ cell_faces,
+    float* __restrict__ out_feat, long long* __restrict__ out_idx) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const long long p = (long long)blockIdx.x * RD_WARPS + warp;
+    if (p >= P) return;
+    float* s_depth = smem + (size_t)warp * Kpad * 4;
+    int* s_face = (int*)(s_depth + Kpad);
+    float* s_w1 = s_depth + 2 * Kpad;
+    float* s_w2 = s_depth + 3 * Kpad;
+    const size_t po = (size_t)b * P + p;
+    const float px = pix[po * 2], py = pix[po * 2 + 1];
+    const float zmin = ranges[po * 2], zmax = ranges[po * 2 + 1];
+    PixGrid g = pix_grid(bbox_ord, b, R);
+    const size_t cell = ((size_t)b * R + pix_cell(py, g.oy, g.inv, R)) * R + pix_cell(px, g.ox, g.inv, R);
+    const unsigned j0 = cell_start[cell], j1 = cell_end[cell];
+    const float* fxy = face_xy + (size_t)b * F * 6;
+    const float* fz = face_z + (size_t)b * F * 3;
+    int count = 0;
+    for (unsigned jb = j0; jb < j1 && count < K; jb += 32) {
+        unsigned j = jb + lane;
+        Bary2 r; r.hit = false;
+        int f = -1;
+        if (j < j1) {
+            f = (int)cell_faces[j];
+            r = face_test(fxy + (size_t)f * 6, fz + (size_t)f * 3, px, py, zmin, zmax, eps);
+        }
+        unsigned hits = __ballot_sync(0xffffffffu, r.hit);
+        if (r.hit) {
+            int slot = count + __popc(hits & ((1u << lane) - 1u));
+            if (slot < K) { s_depth[slot] = r.depth; s_face[slot] = f; s_w1[slot] = r.w1; s_w2[slot] = r.w2; }
+        }
+        count = min(count + __popc(hits), K);
+    }
+    __syncwarp();
+    // pad to a power of two and bitonic-sort by (depth descending, original slot ascending)
+    int n2 = 1;
+    while (n2 < count) n2 <<= 1;
+    for (int i = count + lane; i < n2; i += 32) { s_depth[i] = -3.4e38f; s_face[i] = -1; s_w1[i] = 0.f; s_w2[i] = 0.f; }
+    __syncwarp();
+    // the slot order is encoded by giving equal depths a deterministic order through a stable network on (depth, face id)
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < n2; i += 32) {
+                int l = i ^ j;
+                if (l > i) {
+                    bool up = (i & k) == 0;              // "up" = this half sorted in final (descending-depth) order
+                    float da = s_depth[i], db = s_depth[l];
+                    int fa = s_face[i], fb = s_face[l];
+                    // a should come before b when depth larger, or equal depth and smaller face id (void = -1 sorts last)
+                    bool a_first = (da > db) || (da == db && (unsigned)fa < (unsigned)fb);
+                    if (a_first != up) {
+                        s_depth[i] = db; s_depth[l] = da; s_face[i] = fb; s_face[l] = fa;
+                        float t = s_w1[i]; s_w1[i] = s_w1[l]; s_w1[l] = t;
+                        t = s_w2[i]; s_w2[i] = s_w2[l]; s_w2[l] = t;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    // write the K slots of this pixel
+    long long* oi = out_idx + po * K;
+    for (int k = lane; k < K; k += 32) oi[k] = (k < count) ? (long long)s_face[k] : -1ll;
+    float* of = out_feat + po * (size_t)K * D;
+    const float* ff = face_feat + (size_t)b * F * 3 * D;
+    for (int e = lane; e < K * D; e += 32) {
+        int k = e / D, c = e - k * D;
+        float v = 0.f;
+        if (k < count) {
+            int f = s_face[k];
+            float w1 = s_w1[k], w2 = s_w2[k], w0 = 1.f - w1 - w2;
+            const float* q = ff + (size_t)f * 3 * D;
+            v = w0 * q[c] + w1 * q[D + c] + w2 * q[2 * D + c];
+        }
+        of[e] = v;
+    }
+}
+
+// backward: one thread per (pixel, slot)
+__global__ void __launch_bounds__(256) rd_backward_kernel(const float* __restrict__ pix, const float* __restrict__ face_xy,
+                                                          const float* __restrict__ face_feat, const long long* __restrict__ idx,
+                                                          const float* __restrict__ g_out, int P, int F, int D, int K, float eps,
+                                                          float* __restrict__ g_xy, float* __restrict__ g_feat) {
+    const int b = blockIdx.y;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)P * K) return;
+    const size_t o = (size_t)b * P * K + e;
+    long long f = idx[o];
+    if (f < 0) return;
+    const long long p = e / K;
+    const float px = pix[((size_t)b * P + p) * 2], py = pix[((size_t)b * P + p) * 2 + 1];
+    const float* xy = face_xy + ((size_t)b * F + f) * 6;
+    float ax = xy[0], ay = xy[1], bx = xy[2], by = xy[3], cx = xy[4], cy = xy[5];
+    float m = bx - ax, pp = by - ay, n = cx - ax, q = cy - ay, s = px - ax, t = py - ay;
+    float k1 = s * q - n * t, k2 = m * t - s * pp, k3 = m * q - n * pp;
+    float den = k3 + eps, inv = 1.f / den;
+    float w1 = k1 * inv, w2 = k2 * inv, w0 = 1.f - w1 - w2;
+    const float* go = g_out + o * D;
+    const float* ff = face_feat + ((size_t)b * F + f) * 3 * D;
+    float gw0 = 0.f, gw1 = 0.f, gw2 = 0.f;
+    for (int c = 0; c < D; ++c) {
+        float gc = go[c];
+        gw0 += gc * ff[c]; gw1 += gc * ff[D + c]; gw2 += gc * ff[2 * D + c];
+        if (g_feat) {
+            float* gf = g_feat + ((size_t)b * F + f) * 3 * D;
+            atomicAdd(gf + c, w0 * gc); atomicAdd(gf + D + c, w1 * gc); atomicAdd(gf + 2 * D + c, w2 * gc);
+        }
+    }
+    if (g_xy) {
+        float a1 = gw1 - gw0, a2 = gw2 - gw0;                 // w0 = 1 - w1 - w2
+        float gk1 = a1 * inv, gk2 = a2 * inv, gk3 = -(a1 * k1 + a2 * k2) * inv * inv;
+        float g_s = gk1 * q - gk2 * pp, g_t = -gk1 * n + gk2 * m;
+        float g_m = gk2 * t + gk3 * q, g_pp = -gk2 * s - gk3 * n, g_n = -gk1 * t - gk3 * pp, g_q = gk1 * s + gk3 * m;
+        float* gx = g_xy + ((size_t)b * F + f) * 6;
+        atomicAdd(gx + 0, -(g_m + g_n + g_s)); atomicAdd(gx + 1, -(g_pp + g_q + g_t));
+        atomicAdd(gx + 2, g_m); atomicAdd(gx + 3, g_pp); atomicAdd(gx + 4, g_n); atomicAdd(gx + 5, g_q);
+    }
+}
+
+}  // namespace dtb
+
+using namespace dtb;
+
+static int rd_kpad(int K) { int p = 32; while (p < K) p <<= 1; return p; }
+
+extern "C" size_t dtb_sparse_render_workspace(int B, int P, int F, int R, long long pair_capacity) {
+    (void)P;
+    if (R <= 0) R = 128;
+    if (pair_capacity <= 0) pair_capacity = (long long)B * F * 8;
+    size_t cells = (size_t)B * R * R, n = (size_t)pair_capacity;
+    return align_up((size_t)B * 16, 256) + 2 * align_up((size_t)B * F * 4, 256) + 2 * align_up(cells * 4, 256) + 2 * align_up(n * 8, 256) +
+           2 * align_up(n * 4, 256) + scan_workspace_bytes((size_t)B * F) + scan_workspace_bytes(cells) + sort_workspace_bytes(n) + 2048;
+}
+
+// pixel_coords (B,P,2), render_ranges (B,P,2), face_z (B,F,3), face_xy (B,F,3,2), face_feat (B,F,3,D) ->
+// out_feat (B,P,K,D) f32, out_idx (B,P,K) i64.  R: cells per axis of the face-binning grid (<=0: 128);
+// pair_capacity: room for (cell, face) pairs (<=0: 8 per face); *overflow (device int) is set if it was too small.
+extern "C" int dtb_sparse_render_forward(const float* pixel_coords, const float* render_ranges, const float* face_z, const float* face_xy,
+                                         const float* face_feat, int B, int P, int F, int D, int K, float eps, int R, long long pair_capacity,
+                                         float* out_feat, long long* out_idx, int32_t* overflow, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+    if (B == 0 || P == 0 || K == 0) return DTB_OK;
+    DTB_REQUIRE(pixel_coords && render_ranges && out_feat && out_idx && overflow && D > 0, "sparse_render_forward: bad argument");
+    DTB_REQUIRE(K <= 1024, "sparse_render_forward: K=%d > 1024 not supported", K);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (R <= 0) R = 128;
+    if (pair_capacity <= 0) pair_capacity = (long long)B * F * 8;
+    size_t cells = (size_t)B * R * R, cap = (size_t)pair_capacity;
+    Workspace ws(workspace, workspace_bytes);
+    unsigned* bbox = ws.take<unsigned>((size_t)B * 4);
+    unsigned* npairs = ws.take<unsigned>((size_t)B * F);
+    unsigned* pair_off = ws.take<unsigned>((size_t)B * F);
+    unsigned* cstart = ws.take<unsigned>(cells);
+    unsigned* cend = ws.take<unsigned>(cells);
+    u64* k0 = ws.take<u64>(cap); u64* k1 = ws.take<u64>(cap);
+    unsigned* v0 = ws.take<unsigned>(cap); unsigned* v1 = ws.take<unsigned>(cap);
+    size_t sb1 = scan_workspace_bytes((size_t)B * F), sb2 = scan_workspace_bytes(cells), sob = sort_workspace_bytes(cap);
+    void* sws1 = ws.take<char>(sb1); void* sws2 = ws.take<char>(sb2); void* sows = ws.take<char>(sob);
+    unsigned* total = ws.take<unsigned>(1);
+    if (!ws.ok || !workspace) { set_error("sparse_render: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return DTB_EWORKSPACE; }
+    rd_init_kernel<<<cdiv(B * 4, 64), 64, 0, st>>>(bbox, B);
+    dim3 gp(min(cdiv(P, 256), 128), B);
+    rd_bbox_kernel<<<gp, 256, 0, st>>>(pixel_coords, P, bbox);
+    DTB_LAUNCH_CHECK("rd_bbox");
+    DTB_CUDA(cudaMemsetAsync(cstart, 0, cells * 4, st));
+    DTB_CUDA(cudaMemsetAsync(total, 0, 4, st));
+    if (F > 0) {
+        DTB_REQUIRE(face_z && face_xy && face_feat, "sparse_render_forward: null faces");
+        dim3 gf(cdiv(F, 256), B);
+        rd_count_kernel<<<gf, 256, 0, st>>>(face_xy, F, R, bbox, npairs);
+        DTB_LAUNCH_CHECK("rd_count");
+        int rc = exclusive_scan_u32(npairs, pair_off, (size_t)B * F, total, sws1, sb1, st);
+        if (rc) return rc;
+        rd_pairs_kernel<<<gf, 256, 0, st>>>(face_xy, F, R, bbox, pair_off, cap, k0, v0, cstart);
+        DTB_LAUNCH_CHECK("rd_pairs");
+        rd_pad_kernel<<<cdiv((long long)cap, 256), 256, 0, st>>>(k0, v0, total, cap);
+        DTB_LAUNCH_CHECK("rd_pad");
+        u64 maxkey = (u64)cells * (u64)F;
+        int bits = 1; while (bits < 64 && (maxkey >> bits)) ++bits;
+        rc = radix_sort_pairs_u64(k0, v0, k1, v1, cap, 64 /* padded keys are ~0 */, sows, sob, st);
+        (void)bits;
+        if (rc) return rc;
+    }
+    int rc = exclusive_scan_u32(cstart, cstart, cells, nullptr, sws2, sb2, st);
+    if (rc) return rc;
+    // cell_end = start + count; with a consistent sorted list, end[c] = start[c+1]; derive by shifting
+    rd_cell_end_kernel<<<cdiv((long long)cells, 256), 256, 0, st>>>(cstart, total, cells, cap, cend, overflow);
+    DTB_LAUNCH_CHECK("rd_cell_end");
+    int Kpad = rd_kpad(K);
+    size_t smem = (size_t)RD_WARPS * Kpad * 16;
+    if (smem > 48 * 1024) DTB_CUDA(cudaFuncSetAttribute(rd_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(P, RD_WARPS), B);
+    rd_forward_kernel<<<grid, RD_WARPS * 32, smem, st>>>(pixel_coords, render_ranges, face_z, face_xy, face_feat, P, F, D, K, Kpad, eps, R, bbox,
+                                                         cstart, cend, v1, out_feat, out_idx);
+    DTB_LAUNCH_CHECK("rd_forward");
+    return DTB_OK;
+}
+
+// g_out (B,P,K,D), idx (B,P,K) from forward -> ACCUMULATES into g_xy (B,F,3,2) and g_feat (B,F,3,D) (either may be NULL)
+extern "C" int dtb_sparse_render_backward(const float* pixel_coords, const float* face_xy, const float* face_feat, const long long* idx,
+                                          const float* g_out, int B, int P, int F, int D, int K, float eps, float* g_xy, float* g_feat,
+                                          void* stream) {
+    if (B == 0 || P == 0 || K == 0 || F == 0) return DTB_OK;
+    DTB_REQUIRE(pixel_coords && face_xy && face_feat && idx && g_out, "sparse_render_backward: null argument");
+    dim3 grid(cdiv((long long)P * K, 256), B);
+    rd_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pixel_coords, face_xy, face_feat, idx, g_out, P, F, D, K, eps, g_xy, g_feat);
+    DTB_LAUNCH_CHECK("rd_backward");
+    return DTB_OK;
+}

@@ -1,0 +1,135 @@
+"""Stand-ins for the two Kaolin operations on the hot path, with Kaolin's call signatures:
+
+  deftet_sparse_render(pixel_coords, render_ranges, face_vertices_z, face_vertices_image, face_features, knum=300, eps=1e-8)
+      used at diff_render/diftet_6_subdiv/5_rendereq/deftetrneder.py:97-100
+  check_sign(verts, faces, points, hash_resolution=512)
+      used at layers/DefTet/deftet.py:46, eval.py:239, dataloader.py:92
+and the Laplacian smoothness loss of DefTet.laplacian_sparse (layers/DefTet/deftet.py:340-343).
+
+Kaolin is un-vendored and un-pinned in the reference: parity for these two is defined by oracle/render_oracle.c
+("parity unpinned")."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .search import _f32c
+
+
+@_lib.register_signatures
+def _render_sigs(lib, sig):
+    vp, i, sz, ll, f = C.c_void_p, C.c_int, C.c_size_t, C.c_longlong, C.c_float
+    sig("dtb_sparse_render_workspace", sz, i, i, i, i, ll)
+    sig("dtb_sparse_render_forward", i, vp, vp, vp, vp, vp, i, i, i, i, i, f, i, ll, vp, vp, vp, vp, sz, vp)
+    sig("dtb_sparse_render_backward", i, vp, vp, vp, vp, vp, i, i, i, i, i, f, vp, vp, vp)
+    sig("dtb_check_sign_workspace", sz, i, i, i)
+    sig("dtb_check_sign", i, vp, vp, vp, i, i, i, i, i, vp, vp, sz, vp)
+    sig("dtb_laplacian_forward", i, vp, vp, vp, i, i, i, vp, vp, vp, vp, vp)
+    sig("dtb_laplacian_backward", i, vp, vp, vp, vp, vp, i, i, vp, vp)
+
+
+class _SparseRender(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pixel_coords, render_ranges, face_vertices_z, face_vertices_image, face_features, knum, eps, grid_res):
+        _lib.require_cuda(pixel_coords, face_vertices_image)
+        pix, rng = _f32c(pixel_coords), _f32c(render_ranges)
+        fz, fxy, ff = _f32c(face_vertices_z), _f32c(face_vertices_image), _f32c(face_features)
+        B, P = pix.shape[0], pix.shape[1]
+        F, D = fz.shape[1], ff.shape[-1]
+        dev = pix.device
+        L = _lib.lib()
+        out = torch.empty(B, P, knum, D, device=dev)
+        idx = torch.empty(B, P, knum, device=dev, dtype=torch.int64)
+        overflow = torch.zeros(1, device=dev, dtype=torch.int32)
+        cap = max(B * F * 8, 1024)
+        with torch.cuda.device(dev):
+            for _ in range(6):
+                wsz = L.dtb_sparse_render_workspace(B, P, F, grid_res, cap)
+                ws = torch.empty(wsz, device=dev, dtype=torch.uint8)
+                _lib.check(L.dtb_sparse_render_forward(_lib.ptr(pix), _lib.ptr(rng), _lib.ptr(fz), _lib.ptr(fxy), _lib.ptr(ff), B, P, F, D,
+                                                       knum, eps, grid_res, cap, _lib.ptr(out), _lib.ptr(idx), _lib.ptr(overflow),
+                                                       _lib.ptr(ws), wsz, _lib.stream_ptr()), "dtb_sparse_render_forward")
+                if int(overflow.item()) == 0:
+                    break
+                cap *= 4
+            else:
+                raise _lib.DeftetB200Error("deftet_sparse_render: face-binning capacity exceeded")
+        ctx.save_for_backward(pix, fxy, ff, idx)
+        ctx.eps = eps
+        ctx.mark_non_differentiable(idx)
+        return out, idx
+
+    @staticmethod
+    def backward(ctx, g_out, _g_idx):
+        pix, fxy, ff, idx = ctx.saved_tensors
+        B, P, K = idx.shape
+        F, D = fxy.shape[1], ff.shape[-1]
+        g_out = _f32c(g_out)
+        g_xy = torch.zeros_like(fxy) if ctx.needs_input_grad[3] else None
+        g_ff = torch.zeros_like(ff) if ctx.needs_input_grad[4] else None
+        with torch.cuda.device(pix.device):
+            _lib.check(_lib.lib().dtb_sparse_render_backward(_lib.ptr(pix), _lib.ptr(fxy), _lib.ptr(ff), _lib.ptr(idx), _lib.ptr(g_out), B, P, F,
+                                                             D, K, ctx.eps, _lib.ptr(g_xy), _lib.ptr(g_ff), _lib.stream_ptr()),
+                       "dtb_sparse_render_backward")
+        return None, None, None, g_xy, g_ff, None, None, None
+
+
+def deftet_sparse_render(pixel_coords, render_ranges, face_vertices_z, face_vertices_image, face_features, knum=300, eps=1e-8,
+                         grid_res=0):
+    """-> (face_features_out (B,P,knum,d), face_idx (B,P,knum) long)."""
+    return _SparseRender.apply(pixel_coords, render_ranges, face_vertices_z, face_vertices_image, face_features, int(knum), float(eps),
+                               int(grid_res))
+
+
+def check_sign(verts, faces, points, hash_resolution=512):
+    """verts (B,n,3), faces (m,3) long, points (B,p,3) -> bool (B,p): True where the point is inside the mesh."""
+    _lib.require_cuda(verts, faces, points)
+    v, p = _f32c(verts), _f32c(points)
+    f = faces.to(torch.int32).contiguous()
+    B, n, m, npts = v.shape[0], v.shape[1], f.shape[0], p.shape[1]
+    dev = v.device
+    L = _lib.lib()
+    out = torch.zeros(B, npts, device=dev, dtype=torch.uint8)
+    R = min(int(hash_resolution), 1024)
+    wsz = L.dtb_check_sign_workspace(B, m, R)
+    ws = torch.empty(wsz, device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        _lib.check(L.dtb_check_sign(_lib.ptr(v), _lib.ptr(f), _lib.ptr(p), B, n, m, npts, R, _lib.ptr(out), _lib.ptr(ws), wsz,
+                                    _lib.stream_ptr()), "dtb_check_sign")
+    return out.bool()
+
+
+class _Laplacian(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, offset, edges, weight):
+        d = _f32c(offset)
+        B, V, _ = d.shape
+        E = edges.shape[0]
+        dev = d.device
+        resid = torch.empty_like(d)
+        rows = torch.empty(V + 1, device=dev, dtype=torch.int32)
+        acc = torch.empty(B, device=dev, dtype=torch.float64)
+        loss = torch.empty(B, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().dtb_laplacian_forward(_lib.ptr(d), _lib.ptr(edges), _lib.ptr(weight), B, V, E, _lib.ptr(resid), _lib.ptr(rows),
+                                                        _lib.ptr(acc), _lib.ptr(loss), _lib.stream_ptr()), "dtb_laplacian_forward")
+        ctx.save_for_backward(resid, edges, weight, rows)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        resid, edges, weight, rows = ctx.saved_tensors
+        B, V, _ = resid.shape
+        grad = torch.zeros_like(resid)
+        g = _f32c(g)
+        with torch.cuda.device(resid.device):
+            _lib.check(_lib.lib().dtb_laplacian_backward(_lib.ptr(resid), _lib.ptr(edges), _lib.ptr(weight), _lib.ptr(rows), _lib.ptr(g), B, V,
+                                                         _lib.ptr(grad), _lib.stream_ptr()), "dtb_laplacian_backward")
+        return grad, None, None
+
+
+def laplacian_loss(offset_bxvx3, edges_ex2, weight_e):
+    """``DefTet.laplacian_sparse`` (deftet.py:340-343) on the (edges, 1/deg) list of builders.tet_point_adj."""
+    return _Laplacian.apply(offset_bxvx3, edges_ex2.to(torch.int32).contiguous(), _f32c(weight_e))

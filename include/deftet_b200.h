@@ -210,6 +210,40 @@ int dtb_host_tet_adj_share(const int32_t* tet_list, int32_t* face_edge_p, int32_
 int dtb_host_tet_face_adj(const int32_t* tet_list, int32_t* face_edge_p, int32_t* n_face_edge_p, int n_point, int n_tet);
 int dtb_host_colaps_v(const float* point_p, int32_t* map_array_p, int32_t* inverse_idx_p, int32_t* n_colaps_v_p, int n_point);
 
+/* ---- A15: tet-face volume rasterizer (stand-in for kal.render.mesh.deftet_sparse_render) ---------------------
+ * Call site: diff_render/diftet_6_subdiv/5_rendereq/deftetrneder.py:97-100 (Kaolin itself is third-party and
+ * un-pinned: parity is defined by oracle/render_oracle.c, see DESIGN.md "parity unpinned").
+ * pixel_coords (B,P,2), render_ranges (B,P,2) [zmin,zmax], face_z (B,F,3), face_xy (B,F,3,2), face_feat (B,F,3,D)
+ * -> out_feat (B,P,K,D) f32 and out_idx (B,P,K) i64: per pixel the first K faces (ascending id) containing it with
+ * interpolated z in range, ordered by z descending; void slots are 0 / -1.  eps: kaolin's 1e-8.
+ * R: cells per axis of the face-binning grid (<=0: 128); pair_capacity: capacity for (cell, face) pairs (<=0: 8 per
+ * face); *overflow (device int32) is set to 1 when it was too small (results are then invalid: retry larger).
+ * backward ACCUMULATES into g_xy (B,F,3,2) and g_feat (B,F,3,D); no gradient to z or the pixel. */
+size_t dtb_sparse_render_workspace(int B, int P, int F, int R, long long pair_capacity);
+int dtb_sparse_render_forward(const float* pixel_coords, const float* render_ranges, const float* face_z, const float* face_xy,
+                              const float* face_feat, int B, int P, int F, int D, int K, float eps, int R, long long pair_capacity,
+                              float* out_feat, long long* out_idx, int32_t* overflow, void* workspace, size_t workspace_bytes,
+                              void* stream);
+int dtb_sparse_render_backward(const float* pixel_coords, const float* face_xy, const float* face_feat, const long long* idx,
+                               const float* g_out, int B, int P, int F, int D, int K, float eps, float* g_xy, float* g_feat,
+                               void* stream);
+
+/* ---- A16: inside/outside labels (stand-in for kal.ops.mesh.check_sign, layers/DefTet/deftet.py:46) ------------
+ * verts (B,n,3), faces (m,3) i32 shared by the batch, points (B,p,3) -> out (B,p) u8, 1 = inside (+z ray parity,
+ * half-open edge rule; oracle/render_oracle.c).  R = kaolin's hash_resolution (xy grid; <=0: 256, max 1024).
+ * Synchronises the stream once (capacity check of the triangle-cell list). */
+size_t dtb_check_sign_workspace(int B, int m, int R);
+int dtb_check_sign(const float* verts, const int32_t* faces, const float* points, int B, int n, int m, int p, int R,
+                   unsigned char* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- A17: Laplacian smoothness sum ||(D^-1 A) d - d||^2 (layers/DefTet/deftet.py:340-343) -------------------
+ * d (B,V,3); edges (E,2) + weight (E,) from dtb_tet_point_adj (sorted by row).  resid_ws (B,V,3) and rows_ws (V+1)
+ * are scratch that backward reuses; backward ACCUMULATES into grad (B,V,3). */
+int dtb_laplacian_forward(const float* d, const int32_t* edges, const float* weight, int B, int V, int E, float* resid_ws,
+                          unsigned* rows_ws, double* acc, float* loss, void* stream);
+int dtb_laplacian_backward(const float* resid_ws, const int32_t* edges, const float* weight, const unsigned* rows_ws,
+                           const float* g_loss, int B, int V, float* grad, void* stream);
+
 /* ---- device-wide primitives (exported for the self-tests; also usable by integrators) ----------------- */
 size_t dtb_prim_scan_workspace(size_t n);
 int dtb_prim_exclusive_scan_u32(const unsigned* in, unsigned* out, size_t n, unsigned* total, void* ws, size_t ws_bytes,

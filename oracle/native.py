@@ -141,3 +141,27 @@ def ref_colaps_v(points_nx3):
     res = _drive("colaps", "colaps_v", np.array([n], dtype=np.int32).tobytes() + pts.tobytes(), 1 + 2 * n)
     cnt = int(res[0])
     return res[1:1 + n].copy(), res[1 + n:1 + n + cnt].copy()
+
+
+# ---- Kaolin stand-ins (parity unpinned, see render_oracle.c) ----------------------------------------------------
+def sparse_render(pixel_coords, render_ranges, face_z, face_xy, face_feat, K, eps=1e-8, threads=None):
+    pix, rng, fz, fxy, ff = _f32(pixel_coords), _f32(render_ranges), _f32(face_z), _f32(face_xy), _f32(face_feat)
+    B, P = pix.shape[0], pix.shape[1]
+    F, D = fz.shape[1], ff.shape[-1]
+    out = np.zeros((B, P, K, D), dtype=np.float32)
+    idx = np.full((B, P, K), -1, dtype=np.int64)
+    L = lib()
+    _split(lambda a, b: L.orc_sparse_render(_p(pix), _p(rng), _p(fz), _p(fxy), _p(ff), B, P, F, D, K, C.c_float(eps), _p(out), _p(idx),
+                                            C.c_longlong(a), C.c_longlong(b)), B * P, threads, min_chunk=8)
+    return out, idx
+
+
+def check_sign(verts, faces, points, threads=None):
+    v, p = _f32(verts), _f32(points)
+    f = np.ascontiguousarray(faces, dtype=np.int32)
+    B, n, m, np_ = v.shape[0], v.shape[1], f.shape[0], p.shape[1]
+    out = np.zeros((B, np_), dtype=np.uint8)
+    L = lib()
+    _split(lambda a, b: L.orc_check_sign(_p(v), _p(f), _p(p), B, n, m, np_, _p(out), C.c_longlong(a), C.c_longlong(b)), B * np_, threads,
+           min_chunk=16)
+    return out.astype(bool)
