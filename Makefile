@@ -6,7 +6,16 @@ SRC := $(wildcard deftet_b200/csrc/*.cu)
 OBJ := $(patsubst deftet_b200/csrc/%.cu,build/%.o,$(SRC))
 LIB := deftet_b200/libdeftet_b200.so
 
-all: $(LIB) oracle
+SHIMS := tet_point_adj tet_adj_share tet_face_adj colaps_v
+SHIM_SO := $(foreach n,$(SHIMS),deftet_b200/dropin/utils/lib/$(n)/run.so)
+
+all: $(LIB) shims oracle
+
+shims: $(SHIM_SO)
+
+deftet_b200/dropin/utils/lib/%/run.so: deftet_b200/csrc/shims/run_shim.c $(LIB)
+	gcc -O2 -fPIC -shared -Iinclude -DSHIM_$(shell echo $* | tr a-z A-Z) -o $@ $< -Ldeftet_b200 -ldeftet_b200 -Wl,-rpath,'$$ORIGIN/../../../..'
+
 
 $(LIB): $(OBJ)
 	$(NVCC) -shared $(ARCH) -o $@ $(OBJ) -lcudart
@@ -22,4 +31,4 @@ clean:
 	rm -rf build $(LIB)
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean shims

@@ -211,16 +211,23 @@ extern "C" int dtb_check_sign(const float* verts, const int32_t* faces, const fl
     dim3 gv(min(cdiv(n, 256), 64), B);
     cs_bbox_kernel<<<gv, 256, 0, st>>>(verts, n, bbox);
     DTB_LAUNCH_CHECK("cs_bbox");
-    DTB_CUDA(cudaMemsetAsync(cstart, 0, cells * 4, st));
     dim3 gf(cdiv(m, 256), B);
-    cs_bin_kernel<<<gf, 256, 0, st>>>(verts, n, faces, m, R, bbox, cstart, nullptr, nullptr, 0);
-    DTB_LAUNCH_CHECK("cs_bin_count");
-    int rc = exclusive_scan_u32(cstart, cstart, cells, total, sws, sb, st);
-    if (rc) return rc;
-    unsigned h_total = 0;       // the pair list has a fixed capacity: check it (one small blocking copy, setup-time op)
-    DTB_CUDA(cudaMemcpyAsync(&h_total, total, 4, cudaMemcpyDeviceToHost, st));
-    DTB_CUDA(cudaStreamSynchronize(st));
-    if ((size_t)h_total > cap) { set_error("check_sign: %u (cell, triangle) pairs exceed the workspace capacity %zu; lower R", h_total, cap); return DTB_EOVERFLOW; }
+    // the (cell, triangle) list has a fixed capacity: halve the grid resolution until it fits (setup-time op, one small
+    // blocking copy per attempt)
+    for (;;) {
+        cells = (size_t)B * R * R;
+        DTB_CUDA(cudaMemsetAsync(cstart, 0, cells * 4, st));
+        cs_bin_kernel<<<gf, 256, 0, st>>>(verts, n, faces, m, R, bbox, cstart, nullptr, nullptr, 0);
+        DTB_LAUNCH_CHECK("cs_bin_count");
+        int rc = exclusive_scan_u32(cstart, cstart, cells, total, sws, sb, st);
+        if (rc) return rc;
+        unsigned h_total = 0;
+        DTB_CUDA(cudaMemcpyAsync(&h_total, total, 4, cudaMemcpyDeviceToHost, st));
+        DTB_CUDA(cudaStreamSynchronize(st));
+        if ((size_t)h_total <= cap) break;
+        if (R <= 1) { set_error("check_sign: %u (cell, triangle) pairs exceed the workspace capacity %zu", h_total, cap); return DTB_EOVERFLOW; }
+        R = R > 2 ? R / 2 : 1;
+    }
     DTB_CUDA(cudaMemcpyAsync(cend, cstart, cells * 4, cudaMemcpyDeviceToDevice, st));
     cs_bin_kernel<<<gf, 256, 0, st>>>(verts, n, faces, m, R, bbox, nullptr, cend, list, 1);
     DTB_LAUNCH_CHECK("cs_bin_fill");

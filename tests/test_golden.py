@@ -1,0 +1,93 @@
+"""Pin the oracle to the reference: golden vectors produced by the reference's own code (tests/golden/make_golden.py),
+the reference's compiled builders when oracle/_ref exists, and the known answers of BASELINE.md section 3."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from deftet_b200.grid import acute_lattice_grid, read_tet_file, snap_boundary
+from oracle import builders as orc_b
+from oracle import energies as orc_e
+from oracle import native
+from tests.util import deformed_grid, rel_err
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REF = "/root/reference"
+
+
+def test_energy_oracle_matches_reference_class():
+    z = np.load(os.path.join(GOLD, "energies_res8.npz"))
+    g, pos, tet = deformed_grid(8, 2, seed=int(z["seed"]))
+    assert np.array_equal(pos.numpy(), z["pos"])                       # the synthetic input is reproducible
+    inv = orc_e.tet_inverse_v(torch.from_numpy(g.centred()), tet)
+    assert rel_err(inv, z["inverse_v"]) < 1e-6
+    out = orc_e.energies_with_grad(pos, tet, inv, tuple(z["weights"]))
+    assert rel_err(out["amips"], z["amips"]) < 1e-6
+    assert rel_err(out["edge"], z["edge"]) < 1e-6
+    assert rel_err(out["volvar"], z["volvar"]) < 1e-5
+    assert rel_err(out["grad"], z["grad"]) < 1e-5
+
+
+def test_builder_oracle_matches_reference_outputs():
+    z = np.load(os.path.join(GOLD, "builders_res8.npz"))
+    g = acute_lattice_grid(8)
+    f3, ft2, fs2, bnd = orc_b.tet_to_face(g.n_vert, g.tets)
+    assert np.array_equal(f3, z["f3"]) and np.array_equal(ft2, z["ft2"]) and np.array_equal(fs2, z["fs2"]) and np.array_equal(bnd, z["bnd"])
+    assert np.array_equal(orc_b.tet_adj_share(g.n_vert, g.tets), z["share"])
+    assert np.array_equal(orc_b.tet_face_adj(g.n_vert, g.tets), z["face_adj"])
+    assert np.array_equal(orc_b.tet_to_adj_edges(g.tets), z["point_adj_sorted"])
+    m, inv = orc_b.colaps_v(g.centred()[g.tets.reshape(-1)])
+    assert np.array_equal(m, z["colaps_map"]) and np.array_equal(inv, z["colaps_inv"])
+
+
+@pytest.mark.skipif(native.ref_lib("tet_adj_share") is None, reason="oracle/_ref not built (needs /root/reference at build time)")
+def test_builder_oracle_matches_compiled_reference_libs():
+    g = acute_lattice_grid(12)
+    o, n = native.ref_run_tet_builder("tet_adj_share", g.tets, g.n_vert, g.n_tet * 8, 3)
+    assert np.array_equal(orc_b.tet_adj_share(g.n_vert, g.tets), o[:2 * n])
+    o, n = native.ref_run_tet_builder("tet_face_adj", g.tets, g.n_vert, g.n_tet * 200, 2)
+    assert np.array_equal(orc_b.tet_face_adj(g.n_vert, g.tets), o[:n])
+    rng = np.random.default_rng(1)
+    pts = np.round(rng.random((3000, 3)).astype(np.float32) * 40) / 40 - 0.5
+    pts[::7] *= -0.0
+    m, inv = orc_b.colaps_v(pts)
+    mc, ic = native.ref_colaps_v(pts)
+    assert np.array_equal(m, mc) and np.array_equal(inv, ic)
+
+
+def test_cube40_known_answers_recorded():
+    z = np.load(os.path.join(GOLD, "cube40_known.npz"))
+    assert float(z["amips"]) == 3.0 and abs(float(z["edge"]) - 1.0805563) < 1e-6
+    assert int(z["shared_faces"]) == 92604 and int(z["directed_edges"]) == 118566 and int(z["n_tet"]) == 47472
+
+
+@pytest.mark.reference
+def test_oracle_reproduces_known_answers_on_shipped_cube40():
+    """T0 of SURVEY.md section 7: the reference's shipped grid through the oracle."""
+    v, t = read_tet_file(os.path.join(REF, "diff_render/diftet_6_subdiv/data/cube_40_tet.tet"))
+    assert v.shape[0] == 9472 and t.shape[0] == 47472
+    pos = torch.from_numpy((v - 0.5).astype(np.float32))
+    tet = torch.from_numpy(t)
+    inv = orc_e.tet_inverse_v(pos, tet)
+    soup = orc_e.gather_tets(pos.unsqueeze(0), tet)
+    assert float(orc_e.amips_energy(soup, inv)) == pytest.approx(3.0, abs=2e-6)
+    assert float(orc_e.edge_length(soup)) == pytest.approx(1.0805563, rel=1e-6)
+    assert orc_b.tet_adj_share(v.shape[0], t[:4000]).shape[1] == 3
+
+
+def test_grid_generator_properties():
+    for res in (8, 16):
+        g = acute_lattice_grid(res)
+        a = g.vertices[g.tets]
+        det = np.linalg.det(np.stack([a[:, 1] - a[:, 0], a[:, 2] - a[:, 0], a[:, 3] - a[:, 0]], 1))
+        assert det.min() > 0                                              # positively oriented like the QuarTet grids
+        assert g.vertices.min() == 0.0 and g.vertices.max() == 1.0
+        f3, ft2, _, bnd = orc_b.tet_to_face(g.n_vert, g.tets)
+        assert 2 * f3.shape[0] + bnd.shape[0] == 4 * g.n_tet                # conforming: every face is shared by <= 2 tets
+        deg = np.bincount(orc_b.tet_to_adj_edges(g.tets)[:, 0], minlength=g.n_vert)
+        assert deg.max() <= 14                                            # acute lattice
+        v2, mask = snap_boundary(g.vertices, res)
+        assert np.array_equal(v2, g.vertices) and mask.shape == (g.n_vert, 3)
+    g2 = acute_lattice_grid(8)
+    assert np.array_equal(g2.tets, acute_lattice_grid(8).tets)
