@@ -382,8 +382,9 @@ def roofline_pass(eng, step, scenes, uv, B, T, V, P, S, Fmax, S_face, NSETS, ite
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     sc0 = scenes[0]
     pos = (sc0["pos"] + step.delta.detach().unsqueeze(0)).requires_grad_(True)
-    faces, counts, _ = surface.boundary_faces(eng.face_table, sc0["occ"], Fmax)
-    Fb = float(counts.float().mean().item())
+    fc = [surface.boundary_faces(eng.face_table, sc["occ"], Fmax)[:2] for sc in scenes]      # per input set
+    set_of = {id(sc): k for k, sc in enumerate(scenes)}
+    Fb = float(torch.stack([c.float().mean() for _, c in fc]).mean().item())
     Fs = eng.face_table.n_face
     groups = {}
 
@@ -436,14 +437,17 @@ def roofline_pass(eng, step, scenes, uv, B, T, V, P, S, Fmax, S_face, NSETS, ite
 
     def g_ch(sc, uvk):
         p = (sc["pos"]).requires_grad_(True)
+        faces, counts = fc[set_of[id(sc)]]
         surface.surface_chamfer(p, faces, counts, uvk[0], uvk[1], sc["gt"]).sum().backward()
 
     def g_sd(sc, uvk):
         p = (sc["pos"]).requires_grad_(True)
+        faces, counts = fc[set_of[id(sc)]]
         surface.surface_distance(p, faces, counts, sc["gt"]).sum().backward()
 
     def g_nl(sc, uvk):
         p = (sc["pos"]).requires_grad_(True)
+        faces, counts = fc[set_of[id(sc)]]
         surface.surface_normal_loss(p, faces, counts).sum().backward()
 
     Q = 20 * Fb
