@@ -235,6 +235,119 @@ __global__ void __launch_bounds__(128) nn_query_kernel(const float* __restrict__
 }
 
 
+// ---- tiled 1-NN: one CTA per (group of) target-grid cells holding queries ---------------------------------------
+// The queries are counting-sorted by the cell of the TARGET grid they fall in; the CTA stages the target points of
+// the 3x3x3 surrounding cells in shared memory and every query scans them all (convergent, ~10 instructions per
+// candidate); a query whose minimum cannot be certified against points outside the neighbourhood falls back to
+// the general brick walk.  Same result as the brute-force scan (lexicographic minimum of (distance, index)).
+constexpr int NNT_THREADS = 64;
+constexpr int NNT_CHUNK = 512;
+constexpr int NNT_CELLS_PER_CTA = 4;
+
+__global__ void __launch_bounds__(256) nn_qbin_count_kernel(const float* __restrict__ queries, int Q, int G, const unsigned* __restrict__ bbox_ord,
+                                                            const int32_t* __restrict__ q_counts, int q_mult, unsigned* __restrict__ qcount,
+                                                            unsigned* __restrict__ qcell) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q) return;
+    if (q_counts && i >= q_counts[b] * q_mult) { qcell[(size_t)b * Q + i] = 0xffffffffu; return; }
+    GridParams g = grid_params(bbox_ord, b, G);
+    const float* p = queries + ((size_t)b * Q + i) * 3;
+    unsigned id = (unsigned)b * G * G * G +
+                  cell_index(cell_coord(p[0], g.ox, g.inv_h, G), cell_coord(p[1], g.oy, g.inv_h, G), cell_coord(p[2], g.oz, g.inv_h, G), G, true);
+    qcell[(size_t)b * Q + i] = id;
+    atomicAdd(qcount + id, 1u);
+}
+__global__ void __launch_bounds__(256) nn_qbin_fill_kernel(const float* __restrict__ queries, int Q, const unsigned* __restrict__ qcell,
+                                                           unsigned* __restrict__ qend, float4* __restrict__ qsorted) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q) return;
+    unsigned id = qcell[(size_t)b * Q + i];
+    if (id == 0xffffffffu) return;
+    const float* p = queries + ((size_t)b * Q + i) * 3;
+    unsigned dst = atomicAdd(qend + id, 1u);
+    qsorted[dst] = make_float4(p[0], p[1], p[2], __int_as_float(i));
+}
+
+__global__ void __launch_bounds__(NNT_THREADS) nn_query_tiled_kernel(int Q, int G, const unsigned* __restrict__ bbox_ord,
+                                                                     const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
+                                                                     const float4* __restrict__ sorted, const unsigned long long* __restrict__ mask,
+                                                                     const unsigned* __restrict__ qstart, const unsigned* __restrict__ qend,
+                                                                     const float4* __restrict__ qsorted, int* __restrict__ result) {
+    __shared__ float4 s_pts[NNT_CHUNK];
+    __shared__ unsigned s_rs[27], s_re[27];
+    __shared__ unsigned s_total;
+    const int b = blockIdx.y;
+    const size_t cell_base = (size_t)b * G * G * G;
+    const GridParams g = grid_params(bbox_ord, b, G);
+    const float slack = 1e-3f * g.h + 1e-6f * (fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz) + (float)G * g.h);
+    for (int cc = 0; cc < NNT_CELLS_PER_CTA; ++cc) {
+        const unsigned cell = blockIdx.x * NNT_CELLS_PER_CTA + cc;      // position in the brick-major cell order
+        if (cell >= (unsigned)(G * G * G)) return;
+        const unsigned q0 = qstart[cell_base + cell], q1 = qend[cell_base + cell];
+        if (q0 == q1) continue;                                         // uniform across the CTA
+        // decode brick-major cell id -> (cx, cy, cz)
+        const unsigned nb = (unsigned)G >> 2;
+        const unsigned brick = cell >> 6, k = cell & 63u;
+        const int cx0 = (int)((brick % nb) << 2) + (int)(k & 3u), cy0 = (int)(((brick / nb) % nb) << 2) + (int)((k >> 2) & 3u),
+                  cz0 = (int)((brick / (nb * nb)) << 2) + (int)(k >> 4);
+        __syncthreads();
+        if (threadIdx.x < 27) {
+            int o = threadIdx.x == 0 ? 13 : (threadIdx.x <= 13 ? threadIdx.x - 1 : threadIdx.x);
+            int z = cz0 + o / 9 - 1, y = cy0 + (o / 3) % 3 - 1, x = cx0 + o % 3 - 1;
+            unsigned rs = 0, re = 0;
+            if (z >= 0 && z < G && y >= 0 && y < G && x >= 0 && x < G) {
+                size_t c = cell_base + cell_index(x, y, z, G, true);
+                rs = cell_start[c]; re = cell_end[c];
+            }
+            s_rs[threadIdx.x] = rs; s_re[threadIdx.x] = re;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned t = 0;
+            for (int j = 0; j < 27; ++j) t += s_re[j] - s_rs[j];
+            s_total = t;
+        }
+        __syncthreads();
+        const unsigned total = s_total;
+        for (unsigned qbase = q0; qbase < q1; qbase += NNT_THREADS) {
+            const unsigned qi = qbase + threadIdx.x;
+            const bool active = qi < q1;
+            NnVisitor v{0.f, 0.f, 0.f, 1e20f, 0};
+            int orig = 0;
+            if (active) { float4 q = qsorted[qi]; v.qx = q.x; v.qy = q.y; v.qz = q.z; orig = __float_as_int(q.w); }
+            for (unsigned c0 = 0; c0 < total; c0 += NNT_CHUNK) {
+                __syncthreads();
+                for (unsigned j = threadIdx.x; j < NNT_CHUNK && c0 + j < total; j += NNT_THREADS) {
+                    unsigned off = c0 + j;
+                    int r = 0;
+                    while (off >= s_re[r] - s_rs[r]) { off -= s_re[r] - s_rs[r]; ++r; }
+                    s_pts[j] = sorted[s_rs[r] + off];
+                }
+                __syncthreads();
+                if (active) {
+                    const int n = (int)min((unsigned)NNT_CHUNK, total - c0);
+#pragma unroll 4
+                    for (int j = 0; j < n; ++j) v.item(s_pts[j]);
+                }
+            }
+            if (active) {
+                float db = 3.0e38f;
+                if (cx0 >= 2) db = fminf(db, v.qx - (g.ox + (float)(cx0 - 1) * g.h));
+                if (cx0 + 2 <= G - 1) db = fminf(db, (g.ox + (float)(cx0 + 2) * g.h) - v.qx);
+                if (cy0 >= 2) db = fminf(db, v.qy - (g.oy + (float)(cy0 - 1) * g.h));
+                if (cy0 + 2 <= G - 1) db = fminf(db, (g.oy + (float)(cy0 + 2) * g.h) - v.qy);
+                if (cz0 >= 2) db = fminf(db, v.qz - (g.oz + (float)(cz0 - 1) * g.h));
+                if (cz0 + 2 <= G - 1) db = fminf(db, (g.oz + (float)(cz0 + 2) * g.h) - v.qz);
+                float lb = fmaxf(db - slack, 0.f) * 0.9999f;
+                if (!(lb * lb > v.best)) brick_walk(v.qx, v.qy, v.qz, g, G, 0.0f, cell_start, cell_end, sorted, mask, cell_base, v);
+                result[(size_t)b * Q + orig] = v.bi;
+            }
+        }
+    }
+}
+
 // ---- interpolation of a per-vertex field at the query points through the barycentric weights ----------
 // out[b,p,:] = sum_k w[b,p,k] * field[b, tet[cond[b,p]][k], :]   (zeros where cond < 0)
 __global__ void __launch_bounds__(256) interp_fwd_kernel(const float* __restrict__ field, const int32_t* __restrict__ tet, int V, int C,
@@ -359,17 +472,18 @@ extern "C" int dtb_tet_barycentric_backward(const float* pos, const int32_t* tet
 // ---- A2 -------------------------------------------------------------------------------------------
 extern "C" int dtb_nearest_neighbor_grid_res(int M) {
     // target points usually sample a surface: ~M^(1/2) cells per axis keeps a few points per occupied cell
-    int g = (int)ceil(sqrt((double)(M > 1 ? M : 1)) * 0.2);
+    int g = (int)ceil(sqrt((double)(M > 1 ? M : 1)) * 0.1);
     g = (g + 3) / 4 * 4;                 // brick layout: multiple of 4
     if (g < 4) g = 4;
     if (g > 128) g = 128;
     return g;
 }
 extern "C" size_t dtb_nearest_neighbor_workspace(int B, int Q, int M, int G) {
-    (void)Q;
     if (G <= 0) G = dtb_nearest_neighbor_grid_res(M);
     G = (G + 3) / 4 * 4;
-    return pointgrid_workspace_bytes(B, M, G, true, true);
+    size_t cells = (size_t)B * G * G * G;
+    return pointgrid_workspace_bytes(B, M, G, true, true) + 2 * align_up(cells * 4, 256) + align_up((size_t)B * Q * 4, 256) +
+           align_up((size_t)B * Q * 16, 256) + scan_workspace_bytes(cells) + 512;
 }
 static int nearest_neighbor_impl(const float* queries, const float* points, int32_t* result, int B, int Q, int M, int G,
                                  const int32_t* q_counts, int q_mult, void* workspace, size_t workspace_bytes, void* stream) {
@@ -386,12 +500,29 @@ static int nearest_neighbor_impl(const float* queries, const float* points, int3
     Workspace ws(workspace, workspace_bytes);
     PointGrid pg;
     pointgrid_carve(pg, B, M, G, true, true, ws);
+    const size_t cells = (size_t)B * G * G * G;
+    unsigned* qstart = ws.take<unsigned>(cells);
+    unsigned* qend = ws.take<unsigned>(cells);
+    unsigned* qcell = ws.take<unsigned>((size_t)B * Q);
+    float4* qsorted = ws.take<float4>((size_t)B * Q);
+    size_t qsb = scan_workspace_bytes(cells);
+    void* qsws = ws.take<char>(qsb);
     if (!ws.ok || !workspace) { set_error("nearest_neighbor: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return DTB_EWORKSPACE; }
     int rc = pointgrid_build(pg, points, false, st);
     if (rc) return rc;
-    dim3 grid(cdiv(Q, 128), B);
-    nn_query_kernel<<<grid, 128, 0, st>>>(queries, Q, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask, result, q_counts, q_mult);
-    DTB_LAUNCH_CHECK("nn_query");
+    dim3 gq(cdiv(Q, 256), B);
+    DTB_CUDA(cudaMemsetAsync(qstart, 0, cells * sizeof(unsigned), st));
+    nn_qbin_count_kernel<<<gq, 256, 0, st>>>(queries, Q, G, pg.bbox_ord, q_counts, q_mult, qstart, qcell);
+    DTB_LAUNCH_CHECK("nn_qbin_count");
+    rc = exclusive_scan_u32(qstart, qstart, cells, nullptr, qsws, qsb, st);
+    if (rc) return rc;
+    DTB_CUDA(cudaMemcpyAsync(qend, qstart, cells * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+    nn_qbin_fill_kernel<<<gq, 256, 0, st>>>(queries, Q, qcell, qend, qsorted);
+    DTB_LAUNCH_CHECK("nn_qbin_fill");
+    dim3 grid(cdiv((long long)G * G * G, NNT_CELLS_PER_CTA), B);
+    nn_query_tiled_kernel<<<grid, NNT_THREADS, 0, st>>>(Q, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask, qstart, qend, qsorted,
+                                                        result);
+    DTB_LAUNCH_CHECK("nn_query_tiled");
     return DTB_OK;
 }
 

@@ -164,12 +164,71 @@ __global__ void __launch_bounds__(256) qbin_fill_kernel(const float* __restrict_
     qsorted[dst] = make_float4(p[0], p[1], p[2], __int_as_float(i));
 }
 
+// Query-independent part of cuda_min_triangle_distance / cuda_line_distance, hoisted out of the per-query loop.
+// Every value is produced by the same operation sequence as in tri_distance(), so results stay bit-identical.
+struct FacePre {
+    float a[3], b[3], c[3];
+    float n[3];          // unit normal
+    float na;            // dot(n, a)
+    float k3;
+    float bc1, cb0, ac0, ca1;        // (b1-c1), (c0-b0), (a0-c0), (c1-a1)
+    float ab[3], bcv[3], ac[3];      // edge vectors B-A for the three edges (a,b), (b,c), (a,c)
+    float den_ab, den_bc, den_ac;    // div_nz(dot(BA,BA))
+};
+constexpr int FACEPRE_FLOATS = sizeof(FacePre) / 4;
+
+__device__ __forceinline__ void face_precompute(const float* t, FacePre& f) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { f.a[k] = t[k]; f.b[k] = t[3 + k]; f.c[k] = t[6 + k]; }
+    float r1[3] = {xsub(f.b[0], f.a[0]), xsub(f.b[1], f.a[1]), xsub(f.b[2], f.a[2])};
+    float r2[3] = {xsub(f.c[0], f.a[0]), xsub(f.c[1], f.a[1]), xsub(f.c[2], f.a[2])};
+    float n[3] = {xsub(xmul(r1[1], r2[2]), xmul(r1[2], r2[1])), xsub(xmul(r1[2], r2[0]), xmul(r1[0], r2[2])),
+                  xsub(xmul(r1[0], r2[1]), xmul(r1[1], r2[0]))};
+    float len = div_nz(xsqrt(xadd(xadd(xmul(n[0], n[0]), xmul(n[1], n[1])), xmul(n[2], n[2]))));
+    f.n[0] = xdiv(n[0], len); f.n[1] = xdiv(n[1], len); f.n[2] = xdiv(n[2], len);
+    f.na = xdot(f.n, f.a);
+    f.bc1 = xsub(f.b[1], f.c[1]); f.cb0 = xsub(f.c[0], f.b[0]); f.ac0 = xsub(f.a[0], f.c[0]); f.ca1 = xsub(f.c[1], f.a[1]);
+    f.k3 = xadd(xmul(f.bc1, f.ac0), xmul(f.cb0, xsub(f.a[1], f.c[1])));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { f.ab[k] = xsub(f.b[k], f.a[k]); f.bcv[k] = xsub(f.c[k], f.b[k]); f.ac[k] = xsub(f.c[k], f.a[k]); }
+    f.den_ab = div_nz(xdot(f.ab, f.ab)); f.den_bc = div_nz(xdot(f.bcv, f.bcv)); f.den_ac = div_nz(xdot(f.ac, f.ac));
+}
+__device__ __forceinline__ float line_dist2_pre(const float* A, const float* BA, float den, const float* P) {
+    float PA[3] = {xsub(P[0], A[0]), xsub(P[1], A[1]), xsub(P[2], A[2])};
+    float t = xdiv(xdot(PA, BA), den);
+    float d[3] = {xsub(PA[0], xmul(BA[0], t)), xsub(PA[1], xmul(BA[1], t)), xsub(PA[2], xmul(BA[2], t))};
+    float dist = xdot(d, d);
+    return (t >= 0.f && t <= 1.f) ? dist : -dist;
+}
+// forward-only distance (same value as tri_distance(..., FWD_MAX_DIS, ...))
+__device__ __forceinline__ float tri_distance_pre(const FacePre& f, const float* p) {
+    float t = xsub(f.na, xdot(f.n, p));
+    float ip[3] = {xadd(p[0], xmul(f.n[0], t)), xadd(p[1], xmul(f.n[1], t)), xadd(p[2], xmul(f.n[2], t))};
+    float plane2 = xmul(t, t);
+    if (f.k3 == 0.f) return FWD_MAX_DIS;
+    float ipc0 = xsub(ip[0], f.c[0]), ipc1 = xsub(ip[1], f.c[1]);
+    float k1 = xadd(xmul(f.bc1, ipc0), xmul(f.cb0, ipc1));
+    float k2 = xadd(xmul(f.ac0, ipc1), xmul(f.ca1, ipc0));
+    float l1 = xdiv(k1, f.k3), l2 = xdiv(k2, f.k3), l3 = xsub(xsub(1.0f, l1), l2);
+    if (l1 >= 0.f && l2 >= 0.f && l3 >= 0.f) return plane2;
+    float d12 = line_dist2_pre(f.a, f.ab, f.den_ab, ip), d23 = line_dist2_pre(f.b, f.bcv, f.den_bc, ip), d13 = line_dist2_pre(f.a, f.ac, f.den_ac, ip);
+    if (d12 <= 0.f) d12 = FWD_MAX_DIS;
+    if (d23 <= 0.f) d23 = FWD_MAX_DIS;
+    if (d13 <= 0.f) d13 = FWD_MAX_DIS;
+    float ml = xmin3(d12, d23, d13);
+    float mp = xmin3(pt_dist2(f.a, ip), pt_dist2(f.b, ip), pt_dist2(f.c, ip));
+    return xadd(plane2, (ml < mp) ? ml : mp);
+}
+
 // One CTA per brick of queries: the faces binned in the 3x3x3 surrounding bricks are staged once in shared
-// memory (centroid + 9 coordinates) and every query of the brick filters / evaluates them from there.  A query
-// whose best distance cannot be certified against faces outside that neighbourhood falls back to the
-// general brick walk.  Results are identical to the brute-force scan (lexicographic minimum).
-constexpr int PFD_THREADS = 128;
-constexpr int PFD_CHUNK = 256;      // candidate faces staged per round
+// memory (centroid + the query-independent half of the distance computation) and every query of the brick
+//   1. finds the candidate with the nearest centroid and evaluates it (all lanes together: no divergence, and the
+//      running minimum is tight from the start),
+//   2. re-scans the candidates with a bounding-sphere reject and evaluates the few survivors.
+// A query whose best distance cannot be certified against faces outside the neighbourhood falls back to the general
+// brick walk.  Results are identical to the brute-force scan (lexicographic minimum of (distance, face id)).
+constexpr int PFD_THREADS = 64;
+constexpr int PFD_CHUNK = 192;      // candidate faces staged per round
 
 __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
     int S, const float* __restrict__ soup, const int32_t* __restrict__ counts, int Fmax, int G, const unsigned* __restrict__ bbox_ord,
@@ -178,12 +237,12 @@ __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
     const int32_t* __restrict__ n_always, int always_cap, const unsigned* __restrict__ qstart, const unsigned* __restrict__ qend,
     const float4* __restrict__ qsorted, float* __restrict__ closest_d, float* __restrict__ closest_f) {
     __shared__ float4 s_cen[PFD_CHUNK];
-    __shared__ float s_tri[PFD_CHUNK * 9];
+    __shared__ float s_pre[PFD_CHUNK * FACEPRE_FLOATS];
     __shared__ unsigned s_rs[27], s_re[27];
     __shared__ unsigned s_total;
     const int b = blockIdx.y;
     const int NB = G >> 2;
-    const int brick = blockIdx.x;                       // brick of this sample
+    const int brick = blockIdx.x;
     const size_t qb = (size_t)b * NB * NB * NB + brick;
     const unsigned q0 = qstart[qb], q1 = qend[qb];
     if (q0 == q1) return;
@@ -195,9 +254,10 @@ __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
     const GridParams g = grid_params(bbox_ord, b, G);
     const float rmax = __uint_as_float(rmax_bits[b]) * 1.001f + 1e-7f;
     const bool brute = na > always_cap;
-    // candidate ranges of the 27 neighbouring bricks (a brick's items are contiguous in `sorted`)
     if (threadIdx.x < 27) {
-        int dz = threadIdx.x / 9 - 1, dy = (threadIdx.x / 3) % 3 - 1, dx = threadIdx.x % 3 - 1;
+        // slot 0 = home brick, then the 26 neighbours
+        int o = threadIdx.x == 0 ? 13 : (threadIdx.x <= 13 ? threadIdx.x - 1 : threadIdx.x);
+        int dz = o / 9 - 1, dy = (o / 3) % 3 - 1, dx = o % 3 - 1;
         int z = bz0 + dz, y = by0 + dy, x = bx0 + dx;
         unsigned rs = 0, re = 0;
         if (!brute && nf > 0 && z >= 0 && z < NB && y >= 0 && y < NB && x >= 0 && x < NB) {
@@ -229,7 +289,6 @@ __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
             if (brute) { for (int f = 0; f < nf; ++f) v.face(f); }
             else { for (int k = 0; k < na; ++k) v.face(always[(size_t)b * always_cap + k]); }
         } else { v.p[0] = v.p[1] = v.p[2] = 0.f; }
-        // stage candidates chunk by chunk
         for (unsigned c0 = 0; c0 < total; c0 += PFD_CHUNK) {
             __syncthreads();
             for (unsigned k = threadIdx.x; k < PFD_CHUNK && c0 + k < total; k += PFD_THREADS) {
@@ -238,22 +297,42 @@ __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
                 while (off >= s_re[r] - s_rs[r]) { off -= s_re[r] - s_rs[r]; ++r; }
                 float4 it = sorted[s_rs[r] + off];
                 s_cen[k] = it;
-                const float* t = sb + (size_t)__float_as_int(it.w) * 9;
+                FacePre fp;
+                face_precompute(sb + (size_t)__float_as_int(it.w) * 9, fp);
+                float* dst = s_pre + (size_t)k * FACEPRE_FLOATS;
+                const float* src = reinterpret_cast<const float*>(&fp);
 #pragma unroll
-                for (int m = 0; m < 9; ++m) s_tri[k * 9 + m] = t[m];
+                for (int m = 0; m < FACEPRE_FLOATS; ++m) dst[m] = src[m];
             }
             __syncthreads();
+            const int n = (int)min((unsigned)PFD_CHUNK, total - c0);
+            // pass 1: nearest centroid (convergent), evaluated by every lane at the same time
+            int kn = -1;
+            float dn = 3.0e38f;
             if (active) {
-                const int n = (int)min((unsigned)PFD_CHUNK, total - c0);
                 for (int k = 0; k < n; ++k) {
+                    float4 it = s_cen[k];
+                    float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
+                    float d2 = dx * dx + dy * dy + dz * dz;
+                    if (d2 < dn) { dn = d2; kn = k; }
+                }
+            }
+            if (kn >= 0) {
+                const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)kn * FACEPRE_FLOATS);
+                float d = tri_distance_pre(fp, v.p);
+                int f = __float_as_int(s_cen[kn].w);
+                if (v.best > d || (d == v.best && v.bi >= 0 && f < v.bi)) { v.best = d; v.bi = f; }
+            }
+            // pass 2: everything that the bounding sphere cannot reject
+            if (active) {
+                for (int k = 0; k < n; ++k) {
+                    if (k == kn) continue;
                     float4 it = s_cen[k];
                     float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
                     float lb = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz) - rmax, 0.f) * 0.9999f;
                     if (lb * lb > v.best) continue;
-                    const float* t = s_tri + k * 9;
-                    float a[3] = {t[0], t[1], t[2]}, bb[3] = {t[3], t[4], t[5]}, c[3] = {t[6], t[7], t[8]};
-                    TriHit h;
-                    float d = tri_distance(a, bb, c, v.p, FWD_MAX_DIS, h);
+                    const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_FLOATS);
+                    float d = tri_distance_pre(fp, v.p);
                     int f = __float_as_int(it.w);
                     if (v.best > d || (d == v.best && v.bi >= 0 && f < v.bi)) { v.best = d; v.bi = f; }
                 }

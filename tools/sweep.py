@@ -25,10 +25,10 @@ def main():
     u = torch.sqrt(torch.rand(B, Fmax, 20, device=dev)); v = torch.rand(B, Fmax, 20, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     pos = sc["pos"]
-    for G in (16, 24, 32, 40, 48, 64, 96):
+    for G in (24, 32, 40, 48, 64, 80, 96):
         med, _ = timeit(lambda: surface.surface_distance(pos, faces, counts, sc["gt"], G), 5, 2, flush)
         print("A4 fwd  G=%3d  %.3f ms" % (G, med))
-    for G in (24, 32, 48, 64, 96, 128):
+    for G in (16, 24, 32, 40, 48, 64, 96):
         med, _ = timeit(lambda: surface.surface_chamfer(pos, faces, counts, u, v, sc["gt"], G), 5, 2, flush)
         print("chamfer fwd G=%3d  %.3f ms" % (G, med))
     for G in (24, 32, 48, 63, 80, 100):
