@@ -65,6 +65,9 @@ class Step:
         self.Fmax, self.S_face = Fmax, S_face
         self.delta = torch.zeros(engine.n_vert, 3, device=engine.device, requires_grad=True)
         self.samples = samples
+        w = self.WEIGHTS
+        self.wvec = torch.tensor([w["amips"], w["edge"], w["volume_variance"], w["chamfer"], w["distance"], w["normal"], w["occupancy"]],
+                                 device=engine.device).unsqueeze(-1)
 
     def forward_backward(self, sc, u, v):
         eng = self.eng
@@ -72,13 +75,9 @@ class Step:
         out = eng.losses(pos, sc["occ"], sc["gt"], u, v, sc["pts"])
         cond, bary = out["condition"], out["barycentric"]
         pred = search.tet_interpolate(sc["vfield"].unsqueeze(-1), eng.tet, cond, bary).squeeze(-1)
-        inside = (cond.squeeze(-1) >= 0).float()
-        occ_loss = (((pred - sc["target"]) ** 2) * inside).sum(dim=-1) / inside.sum(dim=-1).clamp(min=1.0)
-        w = self.WEIGHTS
-        per_sample = (w["amips"] * out["amips"] + w["edge"] * out["edge"] + w["volume_variance"] * out["volume_variance"]
-                      + w["chamfer"] * out["chamfer"] + w["distance"] * out["distance"] + w["normal"] * out["normal"]
-                      + w["occupancy"] * occ_loss)
-        loss = per_sample.sum()
+        occ_loss = search.located_mse(pred, sc["target"], cond)
+        terms = torch.stack([out["amips"], out["edge"], out["volume_variance"], out["chamfer"], out["distance"], out["normal"], occ_loss])
+        loss = (terms * self.wvec).sum()
         loss.backward()
         return loss.detach(), out["boundary_counts"], out["boundary_overflow"]
 

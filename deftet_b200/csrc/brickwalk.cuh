@@ -68,4 +68,53 @@ __device__ __forceinline__ void brick_walk(float qx, float qy, float qz, const G
     }
 }
 
+// Warp-synchronous variant: the 32 lanes hold 32 queries that fall in the SAME cell (the caller sorts the queries by
+// cell), so they share one traversal.  A shell / brick / cell is skipped only when every lane can skip it, the items of
+// a visited cell are broadcast-loaded once and evaluated by all lanes -- no divergence, no shared memory.  Lanes
+// without a query must report bound() < 0 (they then always vote "skip").  (bx0,by0,bz0) = home brick of the cell.
+template <typename V>
+__device__ __forceinline__ void brick_walk_warp(float qx, float qy, float qz, int bx0, int by0, int bz0, const GridParams& g, int G, float inflate,
+                                                const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
+                                                const float4* __restrict__ sorted, const unsigned long long* __restrict__ mask,
+                                                size_t cell_base, V& vis) {
+    const unsigned FULL = 0xffffffffu;
+    const int NB = G >> 2;
+    const float bw = 4.0f * g.h;
+    const float slack = 1e-3f * g.h + 1e-6f * (fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz) + (float)G * g.h);
+    const float shrink = inflate + slack;
+    const size_t brick_base = cell_base >> 6;
+    for (int R = 0; R < NB; ++R) {
+        if (R >= 1) {
+            float lb = fmaxf((float)(R - 1) * bw * 0.999f - shrink, 0.f);
+            if (__all_sync(FULL, lb * lb > vis.bound())) break;
+        }
+        const int z0 = max(bz0 - R, 0), z1 = min(bz0 + R, NB - 1), y0 = max(by0 - R, 0), y1 = min(by0 + R, NB - 1);
+        for (int bz = z0; bz <= z1; ++bz) {
+            const bool zface = (bz == bz0 - R) || (bz == bz0 + R);
+            for (int by = y0; by <= y1; ++by) {
+                const bool full = zface || (by == by0 - R) || (by == by0 + R);
+                const int xa = max(bx0 - R, 0), xb = min(bx0 + R, NB - 1);
+                const int step = full ? 1 : max(2 * R, 1);
+                for (int bx = bx0 - R; bx <= bx0 + R; bx += step) {
+                    if (bx < xa || bx > xb) continue;
+                    const size_t brick = ((size_t)bz * NB + by) * NB + bx;
+                    unsigned long long m = __ldg(mask + brick_base + brick);
+                    if (!m) continue;
+                    const float lx = g.ox + (float)bx * bw, ly = g.oy + (float)by * bw, lz = g.oz + (float)bz * bw;
+                    if (__all_sync(FULL, box_dist2(qx, qy, qz, lx, ly, lz, bw, shrink) > vis.bound())) continue;
+                    const size_t c0 = cell_base + brick * 64;
+                    while (m) {
+                        const int k = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const float cxl = lx + (float)(k & 3) * g.h, cyl = ly + (float)((k >> 2) & 3) * g.h, czl = lz + (float)(k >> 4) * g.h;
+                        if (__all_sync(FULL, box_dist2(qx, qy, qz, cxl, cyl, czl, g.h, shrink) > vis.bound())) continue;
+                        const unsigned j0 = __ldg(cell_start + c0 + k), j1 = __ldg(cell_end + c0 + k);
+                        for (unsigned j = j0; j < j1; ++j) vis.item(__ldg(sorted + j));
+                    }
+                }
+            }
+        }
+    }
+}
+
 }  // namespace dtb

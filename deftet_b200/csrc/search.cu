@@ -218,31 +218,9 @@ struct NnVisitor {
     }
 };
 
-__global__ void __launch_bounds__(128) nn_query_kernel(const float* __restrict__ queries, int Q, int G,
-                                                       const unsigned* __restrict__ bbox_ord, const unsigned* __restrict__ cell_start,
-                                                       const unsigned* __restrict__ cell_end, const float4* __restrict__ sorted,
-                                                       const unsigned long long* __restrict__ mask, int* __restrict__ result,
-                                                       const int32_t* __restrict__ q_counts, int q_mult) {
-    const int b = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= Q) return;
-    if (q_counts && i >= q_counts[b] * q_mult) return;
-    const float* qp = queries + ((size_t)b * Q + i) * 3;
-    NnVisitor v{qp[0], qp[1], qp[2], 1e20f, 0};
-    GridParams g = grid_params(bbox_ord, b, G);
-    brick_walk(v.qx, v.qy, v.qz, g, G, 0.0f, cell_start, cell_end, sorted, mask, (size_t)b * G * G * G, v);
-    result[(size_t)b * Q + i] = v.bi;
-}
-
-
-// ---- tiled 1-NN: one CTA per (group of) target-grid cells holding queries ---------------------------------------
-// The queries are counting-sorted by the cell of the TARGET grid they fall in; the CTA stages the target points of
-// the 3x3x3 surrounding cells in shared memory and every query scans them all (convergent, ~10 instructions per
-// candidate); a query whose minimum cannot be certified against points outside the neighbourhood falls back to
-// the general brick walk.  Same result as the brute-force scan (lexicographic minimum of (distance, index)).
-constexpr int NNT_THREADS = 64;
-constexpr int NNT_CHUNK = 512;
-constexpr int NNT_CELLS_PER_CTA = 4;
+// ---- 1-NN: the queries are counting-sorted by the cell of the TARGET grid they fall in, so that the queries a warp
+// processes together start from the same cell and can share one brick walk (brickwalk.cuh: brick_walk_warp).
+constexpr int NNT_CELLS_PER_CTA = 8;
 
 __global__ void __launch_bounds__(256) nn_qbin_count_kernel(const float* __restrict__ queries, int Q, int G, const unsigned* __restrict__ bbox_ord,
                                                             const int32_t* __restrict__ q_counts, int q_mult, unsigned* __restrict__ qcount,
@@ -270,80 +248,33 @@ __global__ void __launch_bounds__(256) nn_qbin_fill_kernel(const float* __restri
     qsorted[dst] = make_float4(p[0], p[1], p[2], __int_as_float(i));
 }
 
-__global__ void __launch_bounds__(NNT_THREADS) nn_query_tiled_kernel(int Q, int G, const unsigned* __restrict__ bbox_ord,
-                                                                     const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
-                                                                     const float4* __restrict__ sorted, const unsigned long long* __restrict__ mask,
-                                                                     const unsigned* __restrict__ qstart, const unsigned* __restrict__ qend,
-                                                                     const float4* __restrict__ qsorted, int* __restrict__ result) {
-    __shared__ float4 s_pts[NNT_CHUNK];
-    __shared__ unsigned s_rs[27], s_re[27];
-    __shared__ unsigned s_total;
+// one warp per group of cells; the (<= 32 at a time) queries of a cell share one traversal (brick_walk_warp)
+__global__ void __launch_bounds__(32) nn_query_cell_kernel(int Q, int G, const unsigned* __restrict__ bbox_ord,
+                                                           const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
+                                                           const float4* __restrict__ sorted, const unsigned long long* __restrict__ mask,
+                                                           const unsigned* __restrict__ qstart, const unsigned* __restrict__ qend,
+                                                           const float4* __restrict__ qsorted, int* __restrict__ result) {
     const int b = blockIdx.y;
     const size_t cell_base = (size_t)b * G * G * G;
     const GridParams g = grid_params(bbox_ord, b, G);
-    const float slack = 1e-3f * g.h + 1e-6f * (fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz) + (float)G * g.h);
+    const unsigned nb = (unsigned)G >> 2;
     for (int cc = 0; cc < NNT_CELLS_PER_CTA; ++cc) {
         const unsigned cell = blockIdx.x * NNT_CELLS_PER_CTA + cc;      // position in the brick-major cell order
         if (cell >= (unsigned)(G * G * G)) return;
         const unsigned q0 = qstart[cell_base + cell], q1 = qend[cell_base + cell];
-        if (q0 == q1) continue;                                         // uniform across the CTA
-        // decode brick-major cell id -> (cx, cy, cz)
-        const unsigned nb = (unsigned)G >> 2;
-        const unsigned brick = cell >> 6, k = cell & 63u;
-        const int cx0 = (int)((brick % nb) << 2) + (int)(k & 3u), cy0 = (int)(((brick / nb) % nb) << 2) + (int)((k >> 2) & 3u),
-                  cz0 = (int)((brick / (nb * nb)) << 2) + (int)(k >> 4);
-        __syncthreads();
-        if (threadIdx.x < 27) {
-            int o = threadIdx.x == 0 ? 13 : (threadIdx.x <= 13 ? threadIdx.x - 1 : threadIdx.x);
-            int z = cz0 + o / 9 - 1, y = cy0 + (o / 3) % 3 - 1, x = cx0 + o % 3 - 1;
-            unsigned rs = 0, re = 0;
-            if (z >= 0 && z < G && y >= 0 && y < G && x >= 0 && x < G) {
-                size_t c = cell_base + cell_index(x, y, z, G, true);
-                rs = cell_start[c]; re = cell_end[c];
-            }
-            s_rs[threadIdx.x] = rs; s_re[threadIdx.x] = re;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned t = 0;
-            for (int j = 0; j < 27; ++j) t += s_re[j] - s_rs[j];
-            s_total = t;
-        }
-        __syncthreads();
-        const unsigned total = s_total;
-        for (unsigned qbase = q0; qbase < q1; qbase += NNT_THREADS) {
+        if (q0 == q1) continue;
+        const unsigned brick = cell >> 6;
+        const int bx0 = (int)(brick % nb), by0 = (int)((brick / nb) % nb), bz0 = (int)(brick / (nb * nb));
+        for (unsigned qbase = q0; qbase < q1; qbase += 32) {
             const unsigned qi = qbase + threadIdx.x;
             const bool active = qi < q1;
-            NnVisitor v{0.f, 0.f, 0.f, 1e20f, 0};
+            NnVisitor v{0.f, 0.f, 0.f, -1.0f, 0};                      // bound < 0: a lane without a query always votes "skip"
             int orig = 0;
-            if (active) { float4 q = qsorted[qi]; v.qx = q.x; v.qy = q.y; v.qz = q.z; orig = __float_as_int(q.w); }
-            for (unsigned c0 = 0; c0 < total; c0 += NNT_CHUNK) {
-                __syncthreads();
-                for (unsigned j = threadIdx.x; j < NNT_CHUNK && c0 + j < total; j += NNT_THREADS) {
-                    unsigned off = c0 + j;
-                    int r = 0;
-                    while (off >= s_re[r] - s_rs[r]) { off -= s_re[r] - s_rs[r]; ++r; }
-                    s_pts[j] = sorted[s_rs[r] + off];
-                }
-                __syncthreads();
-                if (active) {
-                    const int n = (int)min((unsigned)NNT_CHUNK, total - c0);
-#pragma unroll 4
-                    for (int j = 0; j < n; ++j) v.item(s_pts[j]);
-                }
-            }
-            if (active) {
-                float db = 3.0e38f;
-                if (cx0 >= 2) db = fminf(db, v.qx - (g.ox + (float)(cx0 - 1) * g.h));
-                if (cx0 + 2 <= G - 1) db = fminf(db, (g.ox + (float)(cx0 + 2) * g.h) - v.qx);
-                if (cy0 >= 2) db = fminf(db, v.qy - (g.oy + (float)(cy0 - 1) * g.h));
-                if (cy0 + 2 <= G - 1) db = fminf(db, (g.oy + (float)(cy0 + 2) * g.h) - v.qy);
-                if (cz0 >= 2) db = fminf(db, v.qz - (g.oz + (float)(cz0 - 1) * g.h));
-                if (cz0 + 2 <= G - 1) db = fminf(db, (g.oz + (float)(cz0 + 2) * g.h) - v.qz);
-                float lb = fmaxf(db - slack, 0.f) * 0.9999f;
-                if (!(lb * lb > v.best)) brick_walk(v.qx, v.qy, v.qz, g, G, 0.0f, cell_start, cell_end, sorted, mask, cell_base, v);
-                result[(size_t)b * Q + orig] = v.bi;
-            }
+            float4 q = qsorted[active ? qi : q0];
+            v.qx = q.x; v.qy = q.y; v.qz = q.z;
+            if (active) { v.best = 1e20f; orig = __float_as_int(q.w); }
+            brick_walk_warp(v.qx, v.qy, v.qz, bx0, by0, bz0, g, G, 0.0f, cell_start, cell_end, sorted, mask, cell_base, v);
+            if (active) result[(size_t)b * Q + orig] = v.bi;
         }
     }
 }
@@ -395,6 +326,40 @@ __global__ void __launch_bounds__(256) interp_bwd_kernel(const float* __restrict
     if (g_bary) reinterpret_cast<float4*>(g_bary)[o] = gw;
 }
 
+
+// ---- masked mean-squared error over the located points (the occupancy-regression loss on interpolated values) ----
+// loss[b] = sum_i m_i (x_i - t_i)^2 / max(sum_i m_i, 1), m_i = [cond_i >= 0]
+__global__ void __launch_bounds__(256) mmse_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const float* __restrict__ cond, int P,
+                                                       double* __restrict__ acc) {
+    int b = blockIdx.y;
+    double s = 0.0, c = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+        size_t o = (size_t)b * P + i;
+        if (cond[o] >= 0.f) { float d = x[o] - t[o]; s += (double)(d * d); c += 1.0; }
+    }
+    s = warp_sum(s); c = warp_sum(c);
+    __shared__ double ss[8], sc[8];
+    if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sc[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, n = 0;
+        for (int w = 0; w < 8; ++w) { a += ss[w]; n += sc[w]; }
+        atomicAdd(acc + b * 2, a); atomicAdd(acc + b * 2 + 1, n);
+    }
+}
+__global__ void mmse_finalize_kernel(const double* __restrict__ acc, int B, float* __restrict__ loss) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) loss[b] = (float)(acc[b * 2] / fmax(acc[b * 2 + 1], 1.0));
+}
+__global__ void __launch_bounds__(256) mmse_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, const float* __restrict__ cond, int P,
+                                                       const double* __restrict__ acc, const float* __restrict__ g_loss, float* __restrict__ g_x) {
+    int b = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    size_t o = (size_t)b * P + i;
+    float s = 2.f * g_loss[b] / (float)fmax(acc[b * 2 + 1], 1.0);
+    g_x[o] = cond[o] >= 0.f ? s * (x[o] - t[o]) : 0.f;
+}
 }  // namespace dtb
 
 using namespace dtb;
@@ -409,7 +374,10 @@ static int default_grid_res(long long n_items, int lo, int hi) {
 // ---- A1 -------------------------------------------------------------------------------------------
 extern "C" int dtb_point_in_tet_grid_res(int T, int P) {
     (void)P;
-    return default_grid_res(T, 4, 160);
+    // cell edge ~ two tet bounding boxes: fewest (row visits + candidate tests) in the res-70 sweep (tools/sweep.py)
+    int g = default_grid_res(T, 4, 320);
+    g = (g + 1) / 2;
+    return g < 4 ? 4 : g;
 }
 extern "C" size_t dtb_point_in_tet_workspace(int B, int P, int T, int G) {
     if (G <= 0) G = dtb_point_in_tet_grid_res(T, P);
@@ -520,9 +488,8 @@ static int nearest_neighbor_impl(const float* queries, const float* points, int3
     nn_qbin_fill_kernel<<<gq, 256, 0, st>>>(queries, Q, qcell, qend, qsorted);
     DTB_LAUNCH_CHECK("nn_qbin_fill");
     dim3 grid(cdiv((long long)G * G * G, NNT_CELLS_PER_CTA), B);
-    nn_query_tiled_kernel<<<grid, NNT_THREADS, 0, st>>>(Q, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask, qstart, qend, qsorted,
-                                                        result);
-    DTB_LAUNCH_CHECK("nn_query_tiled");
+    nn_query_cell_kernel<<<grid, 32, 0, st>>>(Q, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask, qstart, qend, qsorted, result);
+    DTB_LAUNCH_CHECK("nn_query_cell");
     return DTB_OK;
 }
 
@@ -557,5 +524,30 @@ extern "C" int dtb_tet_interpolate_backward(const float* field, const int32_t* t
     dim3 grid(cdiv(P, 256), B);
     interp_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(field, tet, V, C, cond, bary, P, g_out, g_field, g_bary);
     DTB_LAUNCH_CHECK("interp_bwd");
+    return DTB_OK;
+}
+
+// x, t, cond (B,P); acc (B,2) f64 scratch kept for backward; loss (B,)
+extern "C" int dtb_masked_mse_forward(const float* x, const float* t, const float* cond, int B, int P, double* acc, float* loss, void* stream) {
+    DTB_REQUIRE(acc && loss, "masked_mse_forward: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    DTB_CUDA(cudaMemsetAsync(acc, 0, (size_t)B * 2 * sizeof(double), st));
+    if (P > 0) {
+        DTB_REQUIRE(x && t && cond, "masked_mse_forward: null argument");
+        dim3 grid(min(cdiv(P, 256 * 4), 64), B);
+        mmse_fwd_kernel<<<grid, 256, 0, st>>>(x, t, cond, P, acc);
+        DTB_LAUNCH_CHECK("mmse_fwd");
+    }
+    mmse_finalize_kernel<<<cdiv(B, 64), 64, 0, st>>>(acc, B, loss);
+    DTB_LAUNCH_CHECK("mmse_finalize");
+    return DTB_OK;
+}
+extern "C" int dtb_masked_mse_backward(const float* x, const float* t, const float* cond, const double* acc, const float* g_loss, int B, int P,
+                                       float* g_x, void* stream) {
+    if (P == 0 || B == 0) return DTB_OK;
+    DTB_REQUIRE(x && t && cond && acc && g_loss && g_x, "masked_mse_backward: null argument");
+    dim3 grid(cdiv(P, 256), B);
+    mmse_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, t, cond, P, acc, g_loss, g_x);
+    DTB_LAUNCH_CHECK("mmse_bwd");
     return DTB_OK;
 }

@@ -228,7 +228,8 @@ __device__ __forceinline__ float tri_distance_pre(const FacePre& f, const float*
 // A query whose best distance cannot be certified against faces outside the neighbourhood falls back to the general
 // brick walk.  Results are identical to the brute-force scan (lexicographic minimum of (distance, face id)).
 constexpr int PFD_THREADS = 64;
-constexpr int PFD_CHUNK = 192;      // candidate faces staged per round
+constexpr int PFD_CHUNK = 192;      // candidate faces staged per round (< 256: survivor lists hold uint8 indices)
+constexpr int PFD_LIST = 12;        // survivors remembered per query and chunk
 
 __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
     int S, const float* __restrict__ soup, const int32_t* __restrict__ counts, int Fmax, int G, const unsigned* __restrict__ bbox_ord,
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
     __shared__ float s_pre[PFD_CHUNK * FACEPRE_FLOATS];
     __shared__ unsigned s_rs[27], s_re[27];
     __shared__ unsigned s_total;
+    __shared__ unsigned char s_list[PFD_THREADS][PFD_LIST];
     const int b = blockIdx.y;
     const int NB = G >> 2;
     const int brick = blockIdx.x;
@@ -323,7 +325,8 @@ __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
                 int f = __float_as_int(s_cen[kn].w);
                 if (v.best > d || (d == v.best && v.bi >= 0 && f < v.bi)) { v.best = d; v.bi = f; }
             }
-            // pass 2: everything that the bounding sphere cannot reject
+            // pass 2: collect what the bounding sphere cannot reject (cheap, no evaluation inside the scan) ...
+            int ns = 0;
             if (active) {
                 for (int k = 0; k < n; ++k) {
                     if (k == kn) continue;
@@ -331,10 +334,29 @@ __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
                     float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
                     float lb = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz) - rmax, 0.f) * 0.9999f;
                     if (lb * lb > v.best) continue;
-                    const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_FLOATS);
-                    float d = tri_distance_pre(fp, v.p);
-                    int f = __float_as_int(it.w);
-                    if (v.best > d || (d == v.best && v.bi >= 0 && f < v.bi)) { v.best = d; v.bi = f; }
+                    if (ns < PFD_LIST) { s_list[threadIdx.x][ns++] = (unsigned char)k; }
+                    else {                                   // list full: evaluate on the spot
+                        const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_FLOATS);
+                        float d = tri_distance_pre(fp, v.p);
+                        int f = __float_as_int(it.w);
+                        if (v.best > d || (d == v.best && v.bi >= 0 && f < v.bi)) { v.best = d; v.bi = f; }
+                    }
+                }
+            }
+            // ... then evaluate the j-th survivor of every lane together (lanes stay converged on the long distance code)
+            for (int j = 0; j < PFD_LIST; ++j) {
+                if (!__any_sync(0xffffffffu, j < ns)) break;
+                if (j < ns) {
+                    int k = s_list[threadIdx.x][j];
+                    float4 it = s_cen[k];
+                    float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
+                    float lb = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz) - rmax, 0.f) * 0.9999f;
+                    if (!(lb * lb > v.best)) {
+                        const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_FLOATS);
+                        float d = tri_distance_pre(fp, v.p);
+                        int f = __float_as_int(it.w);
+                        if (v.best > d || (d == v.best && v.bi >= 0 && f < v.bi)) { v.best = d; v.bi = f; }
+                    }
                 }
             }
         }
@@ -474,7 +496,7 @@ __global__ void pfd_fill_none_kernel(float* __restrict__ d, float* __restrict__ 
 }
 
 extern "C" int dtb_point_face_distance_grid_res(int Fmax) {
-    int g = (int)ceil(sqrt((double)(Fmax > 1 ? Fmax : 1)) * 0.5);
+    int g = (int)ceil(sqrt((double)(Fmax > 1 ? Fmax : 1)) * 0.375);
     g = (g + 3) / 4 * 4;
     if (g < 4) g = 4;
     if (g > 128) g = 128;

@@ -24,6 +24,8 @@ def _search_sigs(lib, sig):
     sig("dtb_tet_barycentric_backward", i, vp, vp, vp, vp, vp, i, i, i, i, vp, vp, vp)
     sig("dtb_tet_interpolate_forward", i, vp, vp, vp, vp, i, i, i, i, vp, vp)
     sig("dtb_tet_interpolate_backward", i, vp, vp, vp, vp, vp, i, i, i, i, vp, vp, vp)
+    sig("dtb_masked_mse_forward", i, vp, vp, vp, i, i, vp, vp, vp)
+    sig("dtb_masked_mse_backward", i, vp, vp, vp, vp, vp, i, i, vp, vp)
     sig("dtb_nearest_neighbor_grid_res", i, i)
     sig("dtb_nearest_neighbor_workspace", sz, i, i, i, i)
     sig("dtb_nearest_neighbor", i, vp, vp, vp, i, i, i, i, vp, sz, vp)
@@ -135,6 +137,36 @@ def tet_interpolate(field_bxvxc, tet, cond, bary):
     if tet.dtype != torch.int32:
         tet = tet.to(torch.int32)
     return _TetInterpolate.apply(field_bxvxc, tet.contiguous(), cond.contiguous(), bary)
+
+
+class _MaskedMSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, target, cond):
+        x, target = _f32c(x), _f32c(target)
+        B, P = x.shape
+        acc = torch.empty(B, 2, device=x.device, dtype=torch.float64)
+        loss = torch.empty(B, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().dtb_masked_mse_forward(_lib.ptr(x), _lib.ptr(target), _lib.ptr(cond), B, P, _lib.ptr(acc), _lib.ptr(loss),
+                                                         _lib.stream_ptr()), "dtb_masked_mse_forward")
+        ctx.save_for_backward(x, target, cond, acc)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        x, target, cond, acc = ctx.saved_tensors
+        B, P = x.shape
+        gx = torch.empty_like(x)
+        g = _f32c(g)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().dtb_masked_mse_backward(_lib.ptr(x), _lib.ptr(target), _lib.ptr(cond), _lib.ptr(acc), _lib.ptr(g), B, P,
+                                                          _lib.ptr(gx), _lib.stream_ptr()), "dtb_masked_mse_backward")
+        return gx, None, None
+
+
+def located_mse(pred_bxp, target_bxp, cond_bxpx1):
+    """Mean squared error over the points that fell inside some tet (cond >= 0): -> (B,)."""
+    return _MaskedMSE.apply(pred_bxp, target_bxp, cond_bxpx1.reshape(pred_bxp.shape).contiguous())
 
 
 def paste_occ(pred_tet_occ, condition):

@@ -94,6 +94,12 @@ int dtb_tet_interpolate_forward(const float* field, const int32_t* tet, const fl
 int dtb_tet_interpolate_backward(const float* field, const int32_t* tet, const float* cond, const float* bary,
                                  const float* g_out, int B, int V, int C, int P, float* g_field, float* g_bary, void* stream);
 
+/* Masked MSE over the located points: loss[b] = sum_i [cond_i >= 0] (x_i - t_i)^2 / max(#located, 1); x, t, cond (B,P);
+ * acc (B,2) f64 scratch reused by backward, which overwrites g_x (B,P). */
+int dtb_masked_mse_forward(const float* x, const float* t, const float* cond, int B, int P, double* acc, float* loss, void* stream);
+int dtb_masked_mse_backward(const float* x, const float* t, const float* cond, const double* acc, const float* g_loss, int B, int P,
+                            float* g_x, void* stream);
+
 /* ---- A2: 1-nearest-neighbour index (one-sided chamfer) -----------------------------------------------
  * Replaces nearest_neighbor_cuda.forward(queries, points, result_int32, batch, nq, np, dim=3)
  * (layers/nearest_neighbor/nearest_neighbor.cpp:34-52, kernel nearest_neighbor_cuda.cu:17-55):

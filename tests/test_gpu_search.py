@@ -136,3 +136,20 @@ def test_tet_interpolate_matches_torch_gather():
     cc = cond.clone()
     pasted = search.paste_occ(occ, cc)
     assert float(cc.min()) >= 0 and pasted.shape == (B, P)
+
+
+def test_located_mse():
+    from deftet_b200 import search
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 1000, generator=gen)
+    t = torch.randn(3, 1000, generator=gen)
+    cond = torch.randint(-1, 5, (3, 1000, 1), generator=gen).float()
+    cond[2] = -1.0
+    dx = x.cuda().requires_grad_(True)
+    loss = search.located_mse(dx, t.cuda(), cond.cuda())
+    (loss * torch.tensor([1.0, 2.0, 3.0]).cuda()).sum().backward()
+    rx = x.double().requires_grad_(True)
+    m = (cond.squeeze(-1) >= 0).double()
+    ref = (((rx - t.double()) ** 2) * m).sum(-1) / m.sum(-1).clamp(min=1.0)
+    (ref * torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)).sum().backward()
+    assert rel_err(loss, ref.detach()) < 1e-6 and rel_err(dx.grad, rx.grad) < 1e-6
