@@ -18,6 +18,30 @@ __device__ __forceinline__ float box_dist2(float qx, float qy, float qz, float l
     return d * d;
 }
 
+// occupancy-word masks of the cells of a 4x4x4 brick whose x / y / z index lies in [lo, hi] (0 <= lo <= hi <= 3)
+__device__ __forceinline__ unsigned long long brick_xmask(int lo, int hi) {
+    return (unsigned long long)(((1u << (hi - lo + 1)) - 1u) << lo) * 0x1111111111111111ull;
+}
+__device__ __forceinline__ unsigned long long brick_ymask(int lo, int hi) {
+    unsigned long long m16 = ((1ull << (4 * (hi - lo + 1))) - 1ull) << (4 * lo);
+    return m16 * 0x0001000100010001ull;
+}
+__device__ __forceinline__ unsigned long long brick_zmask(int lo, int hi) {
+    int n = 16 * (hi - lo + 1);
+    unsigned long long m = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+    return m << (16 * lo);
+}
+// cells of the brick at (lx,ly,lz) that the ball (q, r) can reach; 0 if none
+__device__ __forceinline__ unsigned long long brick_reach_mask(float qx, float qy, float qz, float r, float lx, float ly, float lz, float inv_h) {
+    float fx0 = floorf((qx - r - lx) * inv_h), fx1 = floorf((qx + r - lx) * inv_h);
+    float fy0 = floorf((qy - r - ly) * inv_h), fy1 = floorf((qy + r - ly) * inv_h);
+    float fz0 = floorf((qz - r - lz) * inv_h), fz1 = floorf((qz + r - lz) * inv_h);
+    if (fx1 < 0.f || fx0 > 3.f || fy1 < 0.f || fy0 > 3.f || fz1 < 0.f || fz0 > 3.f) return 0ull;
+    int x0 = (int)fmaxf(fx0, 0.f), x1 = (int)fminf(fx1, 3.f), y0 = (int)fmaxf(fy0, 0.f), y1 = (int)fminf(fy1, 3.f);
+    int z0 = (int)fmaxf(fz0, 0.f), z1 = (int)fminf(fz1, 3.f);
+    return brick_xmask(x0, x1) & brick_ymask(y0, y1) & brick_zmask(z0, z1);
+}
+
 // V must provide:  float bound() const   -- current best value (squared distance) for pruning
 //                  void item(const float4& it)  -- evaluate one item (x,y,z = binned position, w = index bits)
 // `inflate`: radius by which an item may extend beyond the position it was binned with (0 for points).
@@ -34,6 +58,13 @@ __device__ __forceinline__ void brick_walk(float qx, float qy, float qz, const G
     const int bx0 = cell_coord(qx, g.ox, g.inv_h, G) >> 2, by0 = cell_coord(qy, g.oy, g.inv_h, G) >> 2,
               bz0 = cell_coord(qz, g.oz, g.inv_h, G) >> 2;
     const size_t brick_base = cell_base >> 6;
+    unsigned home_cell;
+    {   // start with the query's own cell so that the bound is finite before the first brick is filtered
+        home_cell = cell_index(cell_coord(qx, g.ox, g.inv_h, G), cell_coord(qy, g.oy, g.inv_h, G), cell_coord(qz, g.oz, g.inv_h, G), G, true);
+        const size_t hc = cell_base + home_cell;
+        const unsigned j0 = __ldg(cell_start + hc), j1 = __ldg(cell_end + hc);
+        for (unsigned j = j0; j < j1; ++j) vis.item(__ldg(sorted + j));
+    }
     for (int R = 0; R < NB; ++R) {
         if (R >= 1) {
             float lb = fmaxf((float)(R - 1) * bw * 0.999f - shrink, 0.f);
@@ -50,64 +81,19 @@ __device__ __forceinline__ void brick_walk(float qx, float qy, float qz, const G
                     if (bx < xa || bx > xb) continue;
                     const size_t brick = ((size_t)bz * NB + by) * NB + bx;
                     unsigned long long m = __ldg(mask + brick_base + brick);
+                    if (R == 0) m &= ~(1ull << (home_cell & 63u));          // the home cell has been scanned already
                     if (!m) continue;
                     const float lx = g.ox + (float)bx * bw, ly = g.oy + (float)by * bw, lz = g.oz + (float)bz * bw;
                     if (box_dist2(qx, qy, qz, lx, ly, lz, bw, shrink) > vis.bound()) continue;
+                    // keep only the cells inside the bounding cube of the current search ball (radius sqrt(best) + shrink,
+                    // padded by 1 % of a cell against the rounding of the cell assignment)
+                    m &= brick_reach_mask(qx, qy, qz, sqrtf(vis.bound()) * 1.0001f + shrink + 0.01f * g.h, lx, ly, lz, g.inv_h);
                     const size_t c0 = cell_base + brick * 64;
                     while (m) {
                         const int k = __ffsll((long long)m) - 1;
                         m &= m - 1;
                         const float cxl = lx + (float)(k & 3) * g.h, cyl = ly + (float)((k >> 2) & 3) * g.h, czl = lz + (float)(k >> 4) * g.h;
                         if (box_dist2(qx, qy, qz, cxl, cyl, czl, g.h, shrink) > vis.bound()) continue;
-                        const unsigned j0 = __ldg(cell_start + c0 + k), j1 = __ldg(cell_end + c0 + k);
-                        for (unsigned j = j0; j < j1; ++j) vis.item(__ldg(sorted + j));
-                    }
-                }
-            }
-        }
-    }
-}
-
-// Warp-synchronous variant: the 32 lanes hold 32 queries that fall in the SAME cell (the caller sorts the queries by
-// cell), so they share one traversal.  A shell / brick / cell is skipped only when every lane can skip it, the items of
-// a visited cell are broadcast-loaded once and evaluated by all lanes -- no divergence, no shared memory.  Lanes
-// without a query must report bound() < 0 (they then always vote "skip").  (bx0,by0,bz0) = home brick of the cell.
-template <typename V>
-__device__ __forceinline__ void brick_walk_warp(float qx, float qy, float qz, int bx0, int by0, int bz0, const GridParams& g, int G, float inflate,
-                                                const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
-                                                const float4* __restrict__ sorted, const unsigned long long* __restrict__ mask,
-                                                size_t cell_base, V& vis) {
-    const unsigned FULL = 0xffffffffu;
-    const int NB = G >> 2;
-    const float bw = 4.0f * g.h;
-    const float slack = 1e-3f * g.h + 1e-6f * (fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz) + (float)G * g.h);
-    const float shrink = inflate + slack;
-    const size_t brick_base = cell_base >> 6;
-    for (int R = 0; R < NB; ++R) {
-        if (R >= 1) {
-            float lb = fmaxf((float)(R - 1) * bw * 0.999f - shrink, 0.f);
-            if (__all_sync(FULL, lb * lb > vis.bound())) break;
-        }
-        const int z0 = max(bz0 - R, 0), z1 = min(bz0 + R, NB - 1), y0 = max(by0 - R, 0), y1 = min(by0 + R, NB - 1);
-        for (int bz = z0; bz <= z1; ++bz) {
-            const bool zface = (bz == bz0 - R) || (bz == bz0 + R);
-            for (int by = y0; by <= y1; ++by) {
-                const bool full = zface || (by == by0 - R) || (by == by0 + R);
-                const int xa = max(bx0 - R, 0), xb = min(bx0 + R, NB - 1);
-                const int step = full ? 1 : max(2 * R, 1);
-                for (int bx = bx0 - R; bx <= bx0 + R; bx += step) {
-                    if (bx < xa || bx > xb) continue;
-                    const size_t brick = ((size_t)bz * NB + by) * NB + bx;
-                    unsigned long long m = __ldg(mask + brick_base + brick);
-                    if (!m) continue;
-                    const float lx = g.ox + (float)bx * bw, ly = g.oy + (float)by * bw, lz = g.oz + (float)bz * bw;
-                    if (__all_sync(FULL, box_dist2(qx, qy, qz, lx, ly, lz, bw, shrink) > vis.bound())) continue;
-                    const size_t c0 = cell_base + brick * 64;
-                    while (m) {
-                        const int k = __ffsll((long long)m) - 1;
-                        m &= m - 1;
-                        const float cxl = lx + (float)(k & 3) * g.h, cyl = ly + (float)((k >> 2) & 3) * g.h, czl = lz + (float)(k >> 4) * g.h;
-                        if (__all_sync(FULL, box_dist2(qx, qy, qz, cxl, cyl, czl, g.h, shrink) > vis.bound())) continue;
                         const unsigned j0 = __ldg(cell_start + c0 + k), j1 = __ldg(cell_end + c0 + k);
                         for (unsigned j = j0; j < j1; ++j) vis.item(__ldg(sorted + j));
                     }

@@ -218,9 +218,8 @@ struct NnVisitor {
     }
 };
 
-// ---- 1-NN: the queries are counting-sorted by the cell of the TARGET grid they fall in, so that the queries a warp
-// processes together start from the same cell and can share one brick walk (brickwalk.cuh: brick_walk_warp).
-constexpr int NNT_CELLS_PER_CTA = 8;
+// ---- 1-NN: the queries are counting-sorted by the cell of the TARGET grid they fall in, so that the queries of a
+// warp start from the same cell (coherent mask / cell / point loads, similar control flow).
 
 __global__ void __launch_bounds__(256) nn_qbin_count_kernel(const float* __restrict__ queries, int Q, int G, const unsigned* __restrict__ bbox_ord,
                                                             const int32_t* __restrict__ q_counts, int q_mult, unsigned* __restrict__ qcount,
@@ -248,35 +247,32 @@ __global__ void __launch_bounds__(256) nn_qbin_fill_kernel(const float* __restri
     qsorted[dst] = make_float4(p[0], p[1], p[2], __int_as_float(i));
 }
 
-// one warp per group of cells; the (<= 32 at a time) queries of a cell share one traversal (brick_walk_warp)
-__global__ void __launch_bounds__(32) nn_query_cell_kernel(int Q, int G, const unsigned* __restrict__ bbox_ord,
-                                                           const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
-                                                           const float4* __restrict__ sorted, const unsigned long long* __restrict__ mask,
-                                                           const unsigned* __restrict__ qstart, const unsigned* __restrict__ qend,
-                                                           const float4* __restrict__ qsorted, int* __restrict__ result) {
+// per-thread walk; queries come either in their original order (qsorted == nullptr) or cell-sorted
+__global__ void __launch_bounds__(128) nn_query_thread_kernel(const float* __restrict__ queries, int Q, int G, const unsigned* __restrict__ bbox_ord,
+                                                              const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
+                                                              const float4* __restrict__ sorted, const unsigned long long* __restrict__ mask,
+                                                              const float4* __restrict__ qsorted, const unsigned* __restrict__ qstart,
+                                                              const unsigned* __restrict__ qend, const int32_t* __restrict__ q_counts, int q_mult,
+                                                              int* __restrict__ result) {
     const int b = blockIdx.y;
-    const size_t cell_base = (size_t)b * G * G * G;
-    const GridParams g = grid_params(bbox_ord, b, G);
-    const unsigned nb = (unsigned)G >> 2;
-    for (int cc = 0; cc < NNT_CELLS_PER_CTA; ++cc) {
-        const unsigned cell = blockIdx.x * NNT_CELLS_PER_CTA + cc;      // position in the brick-major cell order
-        if (cell >= (unsigned)(G * G * G)) return;
-        const unsigned q0 = qstart[cell_base + cell], q1 = qend[cell_base + cell];
-        if (q0 == q1) continue;
-        const unsigned brick = cell >> 6;
-        const int bx0 = (int)(brick % nb), by0 = (int)((brick / nb) % nb), bz0 = (int)(brick / (nb * nb));
-        for (unsigned qbase = q0; qbase < q1; qbase += 32) {
-            const unsigned qi = qbase + threadIdx.x;
-            const bool active = qi < q1;
-            NnVisitor v{0.f, 0.f, 0.f, -1.0f, 0};                      // bound < 0: a lane without a query always votes "skip"
-            int orig = 0;
-            float4 q = qsorted[active ? qi : q0];
-            v.qx = q.x; v.qy = q.y; v.qz = q.z;
-            if (active) { v.best = 1e20f; orig = __float_as_int(q.w); }
-            brick_walk_warp(v.qx, v.qy, v.qz, bx0, by0, bz0, g, G, 0.0f, cell_start, cell_end, sorted, mask, cell_base, v);
-            if (active) result[(size_t)b * Q + orig] = v.bi;
-        }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q) return;
+    NnVisitor v{0.f, 0.f, 0.f, 1e20f, 0};
+    int orig = i;
+    if (qsorted) {
+        const size_t cells = (size_t)G * G * G;
+        unsigned lo = qstart[(size_t)b * cells], hi = qend[(size_t)b * cells + cells - 1];     // this sample's slice of the sorted queries
+        if ((unsigned)i >= hi - lo) return;
+        float4 q = qsorted[lo + i];
+        v.qx = q.x; v.qy = q.y; v.qz = q.z; orig = __float_as_int(q.w);
+    } else {
+        if (q_counts && i >= q_counts[b] * q_mult) return;
+        const float* qp = queries + ((size_t)b * Q + i) * 3;
+        v.qx = qp[0]; v.qy = qp[1]; v.qz = qp[2];
     }
+    GridParams g = grid_params(bbox_ord, b, G);
+    brick_walk(v.qx, v.qy, v.qz, g, G, 0.0f, cell_start, cell_end, sorted, mask, (size_t)b * G * G * G, v);
+    result[(size_t)b * Q + orig] = v.bi;
 }
 
 // ---- interpolation of a per-vertex field at the query points through the barycentric weights ----------
@@ -487,9 +483,10 @@ static int nearest_neighbor_impl(const float* queries, const float* points, int3
     DTB_CUDA(cudaMemcpyAsync(qend, qstart, cells * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
     nn_qbin_fill_kernel<<<gq, 256, 0, st>>>(queries, Q, qcell, qend, qsorted);
     DTB_LAUNCH_CHECK("nn_qbin_fill");
-    dim3 grid(cdiv((long long)G * G * G, NNT_CELLS_PER_CTA), B);
-    nn_query_cell_kernel<<<grid, 32, 0, st>>>(Q, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask, qstart, qend, qsorted, result);
-    DTB_LAUNCH_CHECK("nn_query_cell");
+    dim3 grid(cdiv(Q, 128), B);
+    nn_query_thread_kernel<<<grid, 128, 0, st>>>(queries, Q, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask, qsorted, qstart, qend,
+                                                 q_counts, q_mult, result);
+    DTB_LAUNCH_CHECK("nn_query_thread_sorted");
     return DTB_OK;
 }
 

@@ -25,15 +25,16 @@ def main():
     u = torch.sqrt(torch.rand(B, Fmax, 20, device=dev)); v = torch.rand(B, Fmax, 20, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     pos = sc["pos"]
-    for G in (24, 32, 40, 48, 64, 80, 96):
+    for G in ((40, 48, 56) if '--nn' in sys.argv else (24, 32, 40, 48, 64, 80, 96)):
         med, _ = timeit(lambda: surface.surface_distance(pos, faces, counts, sc["gt"], G), 5, 2, flush)
         print("A4 fwd  G=%3d  %.3f ms" % (G, med))
-    for G in (16, 24, 32, 40, 48, 64, 96):
+    for G in (24, 32, 40, 48, 64, 80):
         med, _ = timeit(lambda: surface.surface_chamfer(pos, faces, counts, u, v, sc["gt"], G), 5, 2, flush)
         print("chamfer fwd G=%3d  %.3f ms" % (G, med))
-    for G in (24, 32, 48, 63, 80, 100):
-        med, _ = timeit(lambda: search.point_in_tet(pos, eng.tet, sc["pts"], G), 5, 2, flush)
-        print("A1 fwd G=%3d  %.3f ms" % (G, med))
+    if "--a1" in sys.argv:
+        for G in (24, 32, 48, 63, 80, 100):
+            med, _ = timeit(lambda: search.point_in_tet(pos, eng.tet, sc["pts"], G), 5, 2, flush)
+            print("A1 fwd G=%3d  %.3f ms" % (G, med))
 
 
 if __name__ == "__main__":
