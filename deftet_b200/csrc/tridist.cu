@@ -228,7 +228,8 @@ __device__ __forceinline__ float tri_distance_pre(const FacePre& f, const float*
 // A query whose best distance cannot be certified against faces outside the neighbourhood falls back to the general
 // brick walk.  Results are identical to the brute-force scan (lexicographic minimum of (distance, face id)).
 constexpr int PFD_THREADS = 64;
-constexpr int PFD_CHUNK = 192;      // candidate faces staged per round (< 256: survivor lists hold uint8 indices)
+constexpr int PFD_CHUNK = 192;      // staged candidate capacity (< 256: survivor lists hold uint8 indices)
+constexpr int PFD_SCAN = 192;       // candidates of the 27 bricks inspected per staging round (<= PFD_CHUNK)
 constexpr int PFD_LIST = 12;        // survivors remembered per query and chunk
 
 __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
@@ -278,6 +279,14 @@ __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
     const unsigned total = s_total;
     const float bw = 4.0f * g.h;
     const float slack = 1e-3f * g.h + 1e-6f * (fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz) + (float)G * g.h);
+    // only faces whose centroid lies within `reach` of this brick are staged; a query is final when its search ball
+    // (sqrt(best) + rmax) stays inside that region, otherwise it falls back to the general walk
+    const float reach = rmax + 1.25f * g.h;
+    const float lx0 = g.ox + (float)bx0 * bw, ly0 = g.oy + (float)by0 * bw, lz0 = g.oz + (float)bz0 * bw;
+    const float rlo[3] = {lx0 - reach, ly0 - reach, lz0 - reach}, rhi[3] = {lx0 + bw + reach, ly0 + bw + reach, lz0 + bw + reach};
+    const float gmax = (float)G * g.h;
+    __shared__ unsigned s_n;
+    __shared__ unsigned char s_rel[PFD_CHUNK];      // 1 = the centroid distance is a valid upper bound for this face
     for (unsigned qbase = q0; qbase < q1; qbase += PFD_THREADS) {
         const unsigned qi = qbase + threadIdx.x;
         const bool active = qi < q1;
@@ -291,49 +300,52 @@ __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
             if (brute) { for (int f = 0; f < nf; ++f) v.face(f); }
             else { for (int k = 0; k < na; ++k) v.face(always[(size_t)b * always_cap + k]); }
         } else { v.p[0] = v.p[1] = v.p[2] = 0.f; }
-        for (unsigned c0 = 0; c0 < total; c0 += PFD_CHUNK) {
+        float ub = 3.0e38f;                                 // upper bound of the answer: a centroid is a point of its face
+        for (unsigned c0 = 0; c0 < total; c0 += PFD_SCAN) {
+            // ---- stage (compacting): candidates c0 .. c0+PFD_SCAN of the 27 bricks that lie in the reach region ----
             __syncthreads();
-            for (unsigned k = threadIdx.x; k < PFD_CHUNK && c0 + k < total; k += PFD_THREADS) {
-                unsigned off = c0 + k;
-                int r = 0;
-                while (off >= s_re[r] - s_rs[r]) { off -= s_re[r] - s_rs[r]; ++r; }
-                float4 it = sorted[s_rs[r] + off];
-                s_cen[k] = it;
-                FacePre fp;
-                face_precompute(sb + (size_t)__float_as_int(it.w) * 9, fp);
-                float* dst = s_pre + (size_t)k * FACEPRE_FLOATS;
-                const float* src = reinterpret_cast<const float*>(&fp);
+            if (threadIdx.x == 0) s_n = 0;
+            __syncthreads();
+            for (unsigned k0 = 0; k0 < PFD_SCAN && c0 + k0 < total; k0 += PFD_THREADS) {
+                unsigned off = c0 + k0 + threadIdx.x;
+                bool keep = false;
+                float4 it = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k0 + threadIdx.x < PFD_SCAN && off < total) {
+                    int r = 0;
+                    while (off >= s_re[r] - s_rs[r]) { off -= s_re[r] - s_rs[r]; ++r; }
+                    it = sorted[s_rs[r] + off];
+                    keep = it.x >= rlo[0] && it.x <= rhi[0] && it.y >= rlo[1] && it.y <= rhi[1] && it.z >= rlo[2] && it.z <= rhi[2];
+                }
+                unsigned bal = __ballot_sync(0xffffffffu, keep);
+                unsigned base = 0;
+                if ((threadIdx.x & 31) == 0 && bal) base = atomicAdd(&s_n, (unsigned)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (keep) {
+                    unsigned k = base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+                    s_cen[k] = it;
+                    FacePre fp;
+                    face_precompute(sb + (size_t)__float_as_int(it.w) * 9, fp);
+                    float* dst = s_pre + (size_t)k * FACEPRE_FLOATS;
+                    const float* src = reinterpret_cast<const float*>(&fp);
 #pragma unroll
-                for (int m = 0; m < FACEPRE_FLOATS; ++m) dst[m] = src[m];
+                    for (int m = 0; m < FACEPRE_FLOATS; ++m) dst[m] = src[m];
+                    // same reliability rule as face_stats_kernel (unit normal here): unreliable or invisible faces may
+                    // have a reference distance larger than the distance to their centroid
+                    s_rel[k] = (fp.k3 != 0.f && fabsf(fp.n[2]) > 2e-3f) ? 1 : 0;
+                }
             }
             __syncthreads();
-            const int n = (int)min((unsigned)PFD_CHUNK, total - c0);
-            // pass 1: nearest centroid (convergent), evaluated by every lane at the same time
-            int kn = -1;
-            float dn = 3.0e38f;
+            const int n = (int)s_n;
+            // ---- one scan: tighten the upper bound with centroid distances, remember what the bounding sphere cannot reject ----
+            int ns = 0;
             if (active) {
                 for (int k = 0; k < n; ++k) {
                     float4 it = s_cen[k];
                     float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
                     float d2 = dx * dx + dy * dy + dz * dz;
-                    if (d2 < dn) { dn = d2; kn = k; }
-                }
-            }
-            if (kn >= 0) {
-                const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)kn * FACEPRE_FLOATS);
-                float d = tri_distance_pre(fp, v.p);
-                int f = __float_as_int(s_cen[kn].w);
-                if (v.best > d || (d == v.best && v.bi >= 0 && f < v.bi)) { v.best = d; v.bi = f; }
-            }
-            // pass 2: collect what the bounding sphere cannot reject (cheap, no evaluation inside the scan) ...
-            int ns = 0;
-            if (active) {
-                for (int k = 0; k < n; ++k) {
-                    if (k == kn) continue;
-                    float4 it = s_cen[k];
-                    float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
-                    float lb = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz) - rmax, 0.f) * 0.9999f;
-                    if (lb * lb > v.best) continue;
+                    if (s_rel[k]) ub = fminf(ub, d2 * 1.0001f);
+                    float lb = fmaxf(sqrtf(d2) - rmax, 0.f) * 0.9999f;
+                    if (lb * lb > fminf(ub, v.best)) continue;
                     if (ns < PFD_LIST) { s_list[threadIdx.x][ns++] = (unsigned char)k; }
                     else {                                   // list full: evaluate on the spot
                         const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_FLOATS);
@@ -343,15 +355,16 @@ __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
                     }
                 }
             }
-            // ... then evaluate the j-th survivor of every lane together (lanes stay converged on the long distance code)
-            for (int j = 0; j < PFD_LIST; ++j) {
-                if (!__any_sync(0xffffffffu, j < ns)) break;
+            // ---- evaluate the j-th remembered candidate of every lane together (lanes stay converged on the long distance code);
+            //      latest entries first: they were admitted under the tightest bound ----
+            for (int j = PFD_LIST - 1; j >= 0; --j) {
+                if (!__any_sync(0xffffffffu, j < ns)) continue;
                 if (j < ns) {
                     int k = s_list[threadIdx.x][j];
                     float4 it = s_cen[k];
                     float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
                     float lb = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz) - rmax, 0.f) * 0.9999f;
-                    if (!(lb * lb > v.best)) {
+                    if (!(lb * lb > fminf(ub, v.best))) {
                         const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_FLOATS);
                         float d = tri_distance_pre(fp, v.p);
                         int f = __float_as_int(it.w);
@@ -361,14 +374,15 @@ __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
             }
         }
         if (active && !brute && nf > 0) {
-            // certify against faces outside the 3x3x3 neighbourhood: their centroids are at least db away
+            // certify against faces that were not staged: their centroids lie outside the reach region (or outside the
+            // 3x3x3 bricks, which contain it); sides of the region beyond the face grid's bounding box hold no face
             float db = 3.0e38f;
-            if (bx0 >= 2) db = fminf(db, v.p[0] - (g.ox + (float)(bx0 - 1) * bw));
-            if (bx0 + 2 <= NB - 1) db = fminf(db, (g.ox + (float)(bx0 + 2) * bw) - v.p[0]);
-            if (by0 >= 2) db = fminf(db, v.p[1] - (g.oy + (float)(by0 - 1) * bw));
-            if (by0 + 2 <= NB - 1) db = fminf(db, (g.oy + (float)(by0 + 2) * bw) - v.p[1]);
-            if (bz0 >= 2) db = fminf(db, v.p[2] - (g.oz + (float)(bz0 - 1) * bw));
-            if (bz0 + 2 <= NB - 1) db = fminf(db, (g.oz + (float)(bz0 + 2) * bw) - v.p[2]);
+            const float o3[3] = {g.ox, g.oy, g.oz};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (rlo[k] > o3[k]) db = fminf(db, v.p[k] - rlo[k]);
+                if (rhi[k] < o3[k] + gmax) db = fminf(db, rhi[k] - v.p[k]);
+            }
             float lb = fmaxf(db - rmax - slack, 0.f) * 0.9999f;
             if (!(lb * lb > v.best))
                 brick_walk(v.p[0], v.p[1], v.p[2], g, G, rmax, cell_start, cell_end, sorted, mask, cell_base, v);
