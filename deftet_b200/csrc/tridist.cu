@@ -336,18 +336,26 @@ __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
             }
             __syncthreads();
             const int n = (int)s_n;
-            // ---- one scan: tighten the upper bound with centroid distances, remember what the bounding sphere cannot reject ----
-            int ns = 0;
+            // ---- scan 1: upper bound of the answer from the centroid distances (a centroid is a point of its face) ----
             if (active) {
                 for (int k = 0; k < n; ++k) {
                     float4 it = s_cen[k];
                     float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
                     float d2 = dx * dx + dy * dy + dz * dz;
-                    if (s_rel[k]) ub = fminf(ub, d2 * 1.0001f);
-                    float lb = fmaxf(sqrtf(d2) - rmax, 0.f) * 0.9999f;
-                    if (lb * lb > fminf(ub, v.best)) continue;
+                    if (s_rel[k]) ub = fminf(ub, d2);
+                }
+            }
+            // ---- scan 2: remember the candidates the bounding sphere cannot reject against that bound ----
+            int ns = 0;
+            if (active) {
+                const float bound = fminf(ub * 1.0001f, v.best);
+                for (int k = 0; k < n; ++k) {
+                    float4 it = s_cen[k];
+                    float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
+                    float lb = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz) - rmax, 0.f) * 0.9999f;
+                    if (lb * lb > bound) continue;
                     if (ns < PFD_LIST) { s_list[threadIdx.x][ns++] = (unsigned char)k; }
-                    else {                                   // list full: evaluate on the spot
+                    else {                                   // list full (rare): evaluate on the spot
                         const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_FLOATS);
                         float d = tri_distance_pre(fp, v.p);
                         int f = __float_as_int(it.w);
@@ -364,7 +372,7 @@ __global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
                     float4 it = s_cen[k];
                     float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
                     float lb = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz) - rmax, 0.f) * 0.9999f;
-                    if (!(lb * lb > fminf(ub, v.best))) {
+                    if (!(lb * lb > fminf(ub * 1.0001f, v.best))) {
                         const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_FLOATS);
                         float d = tri_distance_pre(fp, v.p);
                         int f = __float_as_int(it.w);
