@@ -30,25 +30,65 @@ class GeometryEngine:
         self.face_table = surface.FaceTable(f3, ft2)
         self.max_boundary_faces = int(max_boundary_faces)
         self.samples_per_face = int(samples_per_face)
+        self._streams = None
 
     def vertex_adjacency(self, normalize=True):
         """Row-normalised vertex adjacency (train_multigpu.py:72-75) as a torch sparse tensor."""
         return builders.tet_to_adj_sparse(self.n_vert, self.tet, normalize)
 
-    def losses(self, pos, occ, gt_points, u, v, query_points=None, want=("energies", "chamfer", "distance", "normal", "occupancy")):
+    def _side_streams(self):
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(4)]
+        return self._streams
+
+    def losses(self, pos, occ, gt_points, u, v, query_points=None, want=("energies", "chamfer", "distance", "normal", "occupancy"),
+               concurrent=True):
         """pos (B,V,3); occ (B,T) in {0,1}; gt_points (B,S,3); u,v (B,Fmax,samples) sampling randoms;
-        query_points (B,P,3) for the point-in-tet query.  Returns a dict; every loss is (B,)."""
+        query_points (B,P,3) for the point-in-tet query.  Returns a dict; every loss is (B,).
+
+        The loss groups are independent of each other (they only share `pos` and the boundary faces) and each of their
+        kernels leaves most issue slots idle (profiles/), so with ``concurrent=True`` they are enqueued on side streams
+        (fork after the inputs, join before returning; autograd replays the same stream assignment in backward).
+        Everything stays capturable in one CUDA graph."""
         out = {}
+        main = torch.cuda.current_stream(self.device)
+        if concurrent:
+            s_en, s_pit, s_ch, s_sd = self._side_streams()
+        else:
+            s_en = s_pit = s_ch = s_sd = main
+        used = []
+
+        def fork(s):
+            if s is not main:
+                s.wait_stream(main)
+                used.append(s)
+            return torch.cuda.stream(s)
+
+        def publish(*tensors):
+            if concurrent:
+                for t in tensors:
+                    t.record_stream(main)
+
         if "energies" in want:
-            out["amips"], out["edge"], out["volume_variance"] = energies.tet_energies(pos, self.tet, self.inverse_v)
+            with fork(s_en):
+                out["amips"], out["edge"], out["volume_variance"] = energies.tet_energies(pos, self.tet, self.inverse_v)
+                publish(out["amips"], out["edge"], out["volume_variance"])
+        if "occupancy" in want and query_points is not None:
+            with fork(s_pit):
+                out["condition"], out["barycentric"] = search.point_in_tet(pos, self.tet, query_points)
+                publish(out["condition"], out["barycentric"])
         faces, counts, overflow = surface.boundary_faces(self.face_table, occ, self.max_boundary_faces)
         out["boundary_faces"], out["boundary_counts"], out["boundary_overflow"] = faces, counts, overflow
         if "chamfer" in want:
-            out["chamfer"] = surface.surface_chamfer(pos, faces, counts, u, v, gt_points)
+            with fork(s_ch):
+                out["chamfer"] = surface.surface_chamfer(pos, faces, counts, u, v, gt_points)
+                publish(out["chamfer"])
         if "distance" in want:
-            out["distance"] = surface.surface_distance(pos, faces, counts, gt_points)
+            with fork(s_sd):
+                out["distance"] = surface.surface_distance(pos, faces, counts, gt_points)
+                publish(out["distance"])
         if "normal" in want:
             out["normal"] = surface.surface_normal_loss(pos, faces, counts)
-        if "occupancy" in want and query_points is not None:
-            out["condition"], out["barycentric"] = search.point_in_tet(pos, self.tet, query_points)
+        for s in used:
+            main.wait_stream(s)
         return out

@@ -145,3 +145,26 @@ def test_engine_surface_losses_and_gradients(res, B):
     assert rel_err(dan, an.detach()) < 1e-5
     assert rel_err(dnl, nl.detach()) < 1e-5
     assert rel_err(dpos.grad, rpos.grad) < 1e-5
+
+
+def test_engine_concurrent_streams_equal_serial():
+    """GeometryEngine.losses on side streams (fork/join) gives the same losses and gradient as the serial order."""
+    from deftet_b200.engine import GeometryEngine
+    g, pos, tet, occ, f3, ft2, gt = _scene(10, 2, 9)
+    eng = GeometryEngine(g.centred(), g.tets, max_boundary_faces=512, device="cuda")
+    assert torch.equal(eng.tet_face_fx3.cpu().long(), f3) and torch.equal(eng.tet_face_tetidx_fx2.cpu().long(), ft2)
+    gen = torch.Generator().manual_seed(1)
+    u = torch.sqrt(torch.rand(2, 512, 20, generator=gen)).cuda()
+    v = torch.rand(2, 512, 20, generator=gen).cuda()
+    pts = ((torch.rand(2, 3000, 3, generator=gen) - 0.5) * 1.05).cuda()
+    res = []
+    for conc in (False, True):
+        p = pos.cuda().requires_grad_(True)
+        out = eng.losses(p, occ.cuda(), gt.cuda(), u, v, pts, concurrent=conc)
+        total = (out["amips"] + out["edge"] + out["chamfer"] + out["distance"] + out["normal"] + (out["barycentric"] ** 2).sum(dim=(1, 2))).sum()
+        total.backward()
+        torch.cuda.synchronize()
+        res.append((float(total), p.grad.clone(), out["condition"].clone()))
+    assert abs(res[0][0] - res[1][0]) < 1e-5 * abs(res[0][0])
+    assert torch.equal(res[0][2], res[1][2])
+    assert rel_err(res[1][1], res[0][1]) < 1e-5
