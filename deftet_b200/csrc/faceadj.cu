@@ -303,9 +303,8 @@ extern "C" int dtb_face_adjacency(const float* soup, const int32_t* faces, const
         fa_index_group_kernel<<<gc, 256, 0, st>>>(faces, counts, Fmax, V, group, gstart);
         DTB_LAUNCH_CHECK("fa_index_group");
     }
-    int rc = exclusive_scan_u32(gstart, gstart, (size_t)B * NG, nullptr, sws, sb, st);
+    int rc = exclusive_scan_u32_dup(gstart, gstart, gend, (size_t)B * NG, nullptr, sws, sb, st);
     if (rc) return rc;
-    DTB_CUDA(cudaMemcpyAsync(gend, gstart, (size_t)B * NG * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
     fa_fill_kernel<<<gc, 256, 0, st>>>(group, counts, Fmax, NG, gend, glist);
     DTB_LAUNCH_CHECK("fa_fill");
     dim3 gf(cdiv(Fmax, 128), B);

@@ -13,11 +13,6 @@ __device__ __forceinline__ void load_item(const float* items, size_t i, bool tri
     }
 }
 
-__global__ void pg_init_kernel(unsigned* bbox_ord, int B) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B * 6) bbox_ord[i] = ((i % 6) < 3) ? 0xffffffffu : 0u;
-}
-
 __global__ void __launch_bounds__(256) pg_bbox_kernel(const float* __restrict__ items, bool tri, int N, const int32_t* __restrict__ counts, unsigned* __restrict__ bbox_ord) {
     int b = blockIdx.y;
     const int n = counts ? min(counts[b], N) : N;
@@ -43,19 +38,9 @@ __global__ void __launch_bounds__(256) pg_bbox_kernel(const float* __restrict__ 
         float a = s_mn[0][k], c = s_mx[0][k];
         for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a = fminf(a, s_mn[w][k]); c = fmaxf(c, s_mx[w][k]); }
         if (a <= c) {
-            atomicMin(&bbox_ord[(size_t)b * 6 + k], f2ord(a));
+            atomicMax(&bbox_ord[(size_t)b * 6 + k], ~f2ord(a));
             atomicMax(&bbox_ord[(size_t)b * 6 + 3 + k], f2ord(c));
         }
-    }
-}
-
-// if a sample had no finite item the encoded box is still (max,min): make it a unit box at the origin
-__global__ void pg_fix_bbox_kernel(unsigned* bbox_ord, int B) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    unsigned* q = bbox_ord + (size_t)b * 6;
-    if (q[0] == 0xffffffffu || q[3] == 0u) {
-        for (int k = 0; k < 3; ++k) { q[k] = f2ord(0.0f); q[3 + k] = f2ord(1.0f); }
     }
 }
 
@@ -129,8 +114,10 @@ size_t pointgrid_workspace_bytes(int B, int N, int G, bool with_mask, bool brick
 bool pointgrid_carve(PointGrid& pg, int B, int N, int G, bool with_mask, bool brick, Workspace& ws) {
     pg.B = B; pg.N = N; pg.G = G; pg.W = (G + 63) / 64; pg.brick = brick;
     size_t cells = (size_t)B * G * G * G;
+    // bbox_ord and cell_start are adjacent (bbox padded to 256 B) so that one memset clears both
     pg.bbox_ord = ws.take<unsigned>((size_t)B * 6);
     pg.cell_start = ws.take<unsigned>(cells);
+    pg.clear_bytes = ws.base ? (size_t)((char*)(pg.cell_start + cells) - (char*)pg.bbox_ord) : 0;
     pg.cell_end = ws.take<unsigned>(cells);
     pg.sorted = ws.take<float4>((size_t)B * N);
     pg.cell_of = ws.take<unsigned>((size_t)B * N);
@@ -146,24 +133,19 @@ int pointgrid_build_ragged(PointGrid& pg, const float* items, bool tri, const in
     const int B = pg.B, N = pg.N, G = pg.G;
     size_t cells = (size_t)B * G * G * G;
     if (cells >= (1ull << 31) || (size_t)B * N >= (1ull << 31)) { set_error("pointgrid: problem too large for 32-bit cell ids"); return DTB_EOVERFLOW; }
-    pg_init_kernel<<<cdiv(B * 6, 128), 128, 0, st>>>(pg.bbox_ord, B);
-    DTB_LAUNCH_CHECK("pg_init");
-    DTB_CUDA(cudaMemsetAsync(pg.cell_start, 0, cells * sizeof(unsigned), st));
+    DTB_CUDA(cudaMemsetAsync(pg.bbox_ord, 0, pg.clear_bytes, st));
     if (N > 0) {
         dim3 gb(min(cdiv(N, 256 * 8), 64), B);
         pg_bbox_kernel<<<gb, 256, 0, st>>>(items, tri, N, counts, pg.bbox_ord);
         DTB_LAUNCH_CHECK("pg_bbox");
     }
-    pg_fix_bbox_kernel<<<cdiv(B, 128), 128, 0, st>>>(pg.bbox_ord, B);
-    DTB_LAUNCH_CHECK("pg_fix_bbox");
     if (N > 0) {
         dim3 gc(cdiv(N, 256), B);
         pg_count_kernel<<<gc, 256, 0, st>>>(items, tri, N, G, pg.brick, counts, pg.bbox_ord, pg.cell_start, pg.cell_of);
         DTB_LAUNCH_CHECK("pg_count");
     }
-    int rc = exclusive_scan_u32(pg.cell_start, pg.cell_start, cells, nullptr, pg.scan_ws, pg.scan_ws_bytes, st);
+    int rc = exclusive_scan_u32_dup(pg.cell_start, pg.cell_start, pg.cell_end, cells, nullptr, pg.scan_ws, pg.scan_ws_bytes, st);
     if (rc) return rc;
-    DTB_CUDA(cudaMemcpyAsync(pg.cell_end, pg.cell_start, cells * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
     if (N > 0) {
         dim3 gc(cdiv(N, 256), B);
         pg_fill_kernel<<<gc, 256, 0, st>>>(items, tri, N, counts, pg.cell_of, pg.cell_end, pg.sorted);

@@ -30,12 +30,16 @@ struct PointGrid {
     unsigned* cell_of;        // [B*N] scratch (cell id per item)
     unsigned long long* mask; // [B*G*G*W] or nullptr
     void* scan_ws; size_t scan_ws_bytes;
+    size_t clear_bytes;       // bbox_ord .. end of cell_start (zeroed by one memset)
 };
 
 __device__ __forceinline__ GridParams grid_params(const unsigned* bbox_ord, int b, int G) {
+    // bbox_ord is zero-initialised (one memset together with the cell counters): slots 0-2 hold ~ord(min) so that
+    // atomicMax works for the minimum too; an untouched box (no finite item) reads as the unit box at the origin
     const unsigned* q = bbox_ord + (size_t)b * 6;
     GridParams g;
-    g.ox = ord2f(q[0]); g.oy = ord2f(q[1]); g.oz = ord2f(q[2]);
+    if (q[3] == 0u || q[0] == 0u) { g.ox = g.oy = g.oz = 0.f; g.inv_h = (float)G; g.h = 1.0f / (float)G; return g; }
+    g.ox = ord2f(~q[0]); g.oy = ord2f(~q[1]); g.oz = ord2f(~q[2]);
     float ex = ord2f(q[3]) - g.ox, ey = ord2f(q[4]) - g.oy, ez = ord2f(q[5]) - g.oz;
     float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-20f));
     ext = ext * (1.0f + 9.5367431640625e-7f);

@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const unsigne
 
 // scans one tile per block; adds block_offsets[blockIdx.x] when given
 __global__ void __launch_bounds__(SCAN_THREADS) scan_down_kernel(const unsigned* __restrict__ in, unsigned* __restrict__ out, size_t n,
-                                                                 const unsigned* __restrict__ block_offsets, unsigned* __restrict__ total) {
+                                                                 const unsigned* __restrict__ block_offsets, unsigned* __restrict__ total,
+                                                                 unsigned* __restrict__ out2) {
     __shared__ unsigned s_warp[33];
     size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
     unsigned v[SCAN_ITEMS];
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_down_kernel(const unsigned*
     ex += off;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
-        if (base + k < n) out[base + k] = ex;
+        if (base + k < n) { out[base + k] = ex; if (out2) out2[base + k] = ex; }
         ex += v[k];
     }
     if (total && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total = off + btot;
@@ -93,12 +94,17 @@ size_t scan_workspace_bytes(size_t n) {
 }
 
 int exclusive_scan_u32(const unsigned* in, unsigned* out, size_t n, unsigned* total, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return exclusive_scan_u32_dup(in, out, nullptr, n, total, ws, ws_bytes, st);
+}
+
+int exclusive_scan_u32_dup(const unsigned* in, unsigned* out, unsigned* out2, size_t n, unsigned* total, void* ws, size_t ws_bytes,
+                           cudaStream_t st) {
     if (n == 0) {
         if (total) DTB_CUDA(cudaMemsetAsync(total, 0, sizeof(unsigned), st));
         return DTB_OK;
     }
     if (n <= (size_t)SCAN_TILE) {
-        scan_down_kernel<<<1, SCAN_THREADS, 0, st>>>(in, out, n, nullptr, total);
+        scan_down_kernel<<<1, SCAN_THREADS, 0, st>>>(in, out, n, nullptr, total, out2);
         DTB_LAUNCH_CHECK("scan_down");
         return DTB_OK;
     }
@@ -110,7 +116,7 @@ int exclusive_scan_u32(const unsigned* in, unsigned* out, size_t n, unsigned* to
     DTB_LAUNCH_CHECK("scan_reduce");
     int rc = exclusive_scan_u32(sums, sums, nb, nullptr, (char*)ws + need, ws_bytes - need, st);
     if (rc) return rc;
-    scan_down_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, sums, total);
+    scan_down_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, sums, total, out2);
     DTB_LAUNCH_CHECK("scan_down");
     return DTB_OK;
 }

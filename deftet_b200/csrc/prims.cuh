@@ -23,6 +23,9 @@ __device__ __forceinline__ float ord2f(unsigned u) {
 // Workspace: scan_workspace_bytes(n).  Three launches per level (reduce / scan block sums / downsweep).
 size_t scan_workspace_bytes(size_t n);
 int exclusive_scan_u32(const unsigned* in, unsigned* out, size_t n, unsigned* total, void* ws, size_t ws_bytes, cudaStream_t st);
+// same, additionally writing a copy of the result to out2 (saves the cell_end = cell_start memcpy of the counting sorts)
+int exclusive_scan_u32_dup(const unsigned* in, unsigned* out, unsigned* out2, size_t n, unsigned* total, void* ws, size_t ws_bytes,
+                           cudaStream_t st);
 
 // ---- radix sort ------------------------------------------------------------------------------------
 // Stable LSD sort of (key64, val32) pairs on key bits [0, key_bits).  Result ends in keys_out/vals_out.

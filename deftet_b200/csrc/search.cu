@@ -478,9 +478,8 @@ static int nearest_neighbor_impl(const float* queries, const float* points, int3
     DTB_CUDA(cudaMemsetAsync(qstart, 0, cells * sizeof(unsigned), st));
     nn_qbin_count_kernel<<<gq, 256, 0, st>>>(queries, Q, G, pg.bbox_ord, q_counts, q_mult, qstart, qcell);
     DTB_LAUNCH_CHECK("nn_qbin_count");
-    rc = exclusive_scan_u32(qstart, qstart, cells, nullptr, qsws, qsb, st);
+    rc = exclusive_scan_u32_dup(qstart, qstart, qend, cells, nullptr, qsws, qsb, st);
     if (rc) return rc;
-    DTB_CUDA(cudaMemcpyAsync(qend, qstart, cells * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
     nn_qbin_fill_kernel<<<gq, 256, 0, st>>>(queries, Q, qcell, qend, qsorted);
     DTB_LAUNCH_CHECK("nn_qbin_fill");
     dim3 grid(cdiv(Q, 128), B);

@@ -228,11 +228,14 @@ __device__ __forceinline__ float tri_distance_pre(const FacePre& f, const float*
 // A query whose best distance cannot be certified against faces outside the neighbourhood falls back to the general
 // brick walk.  Results are identical to the brute-force scan (lexicographic minimum of (distance, face id)).
 constexpr int PFD_THREADS = 64;
-constexpr int PFD_CHUNK = 192;      // staged candidate capacity (< 256: survivor lists hold uint8 indices)
-constexpr int PFD_SCAN = 192;       // candidates of the 27 bricks inspected per staging round (<= PFD_CHUNK)
+#ifndef PFD_MIN_CTAS
+#define PFD_MIN_CTAS 12
+#endif
+constexpr int PFD_CHUNK = 128;      // staged candidate capacity (< 256: survivor lists hold uint8 indices)
+constexpr int PFD_SCAN = 128;       // candidates of the 27 bricks inspected per staging round (<= PFD_CHUNK)
 constexpr int PFD_LIST = 12;        // survivors remembered per query and chunk
 
-__global__ void __launch_bounds__(PFD_THREADS) pfd_forward_tiled_kernel(
+__global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_kernel(
     int S, const float* __restrict__ soup, const int32_t* __restrict__ counts, int Fmax, int G, const unsigned* __restrict__ bbox_ord,
     const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end, const float4* __restrict__ sorted,
     const unsigned long long* __restrict__ mask, const unsigned* __restrict__ rmax_bits, const int32_t* __restrict__ always,
@@ -518,7 +521,7 @@ __global__ void pfd_fill_none_kernel(float* __restrict__ d, float* __restrict__ 
 }
 
 extern "C" int dtb_point_face_distance_grid_res(int Fmax) {
-    int g = (int)ceil(sqrt((double)(Fmax > 1 ? Fmax : 1)) * 0.375);
+    int g = (int)ceil(sqrt((double)(Fmax > 1 ? Fmax : 1)) * 0.4375);
     g = (g + 3) / 4 * 4;
     if (g < 4) g = 4;
     if (g > 128) g = 128;
@@ -575,9 +578,8 @@ extern "C" int dtb_point_face_distance_forward(const float* points, const float*
         DTB_CUDA(cudaMemsetAsync(qstart, 0, nbr * sizeof(unsigned), st));
         qbin_count_kernel<<<gq, 256, 0, st>>>(points, S, G, pg.bbox_ord, qstart, qbrick);
         DTB_LAUNCH_CHECK("qbin_count");
-        int rc = exclusive_scan_u32(qstart, qstart, nbr, nullptr, qsws, qsb, st);
+        int rc = exclusive_scan_u32_dup(qstart, qstart, qend, nbr, nullptr, qsws, qsb, st);
         if (rc) return rc;
-        DTB_CUDA(cudaMemcpyAsync(qend, qstart, nbr * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
         qbin_fill_kernel<<<gq, 256, 0, st>>>(points, S, qbrick, qend, qsorted);
         DTB_LAUNCH_CHECK("qbin_fill");
     }
