@@ -17,7 +17,37 @@ int check_cuda(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     return (int)e;
 }
+
+struct ProfSlot { cudaEvent_t a = nullptr, b = nullptr; bool recorded = false; };
+static thread_local ProfSlot g_prof[PROF_NTAGS];
+static thread_local int g_prof_on = 0;
+void prof_begin(int tag, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfSlot& p = g_prof[tag];
+    if (!p.a) { cudaEventCreate(&p.a); cudaEventCreate(&p.b); }
+    cudaEventRecord(p.a, st);
+}
+void prof_end(int tag, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfSlot& p = g_prof[tag];
+    if (!p.a) return;
+    cudaEventRecord(p.b, st);
+    p.recorded = true;
+}
 }  // namespace dtb
+
+// Per-kernel timing hooks: dtb_profile_enable(1) makes the library bracket its dominant kernels with CUDA events on the
+// launching stream; dtb_profile_elapsed(tag, &ms) synchronises on the stop event and returns the last duration.
+// Tags: 0 energies_fwd, 1 energies_bwd, 2 pit_tet, 3 nn_query, 4 pfd_forward, 5 bary_backward.
+extern "C" int dtb_profile_enable(int on) { dtb::g_prof_on = on; return 0; }
+extern "C" int dtb_profile_elapsed(int tag, float* ms) {
+    if (tag < 0 || tag >= dtb::PROF_NTAGS || !ms) { dtb::set_error("profile_elapsed: bad tag"); return dtb::DTB_EINVAL; }
+    dtb::ProfSlot& p = dtb::g_prof[tag];
+    if (!p.recorded) { *ms = -1.f; return 0; }
+    DTB_CUDA(cudaEventSynchronize(p.b));
+    DTB_CUDA(cudaEventElapsedTime(ms, p.a, p.b));
+    return 0;
+}
 
 extern "C" const char* dtb_last_error(void) { return dtb::g_err; }
 extern "C" int dtb_version(void) { return 100; }

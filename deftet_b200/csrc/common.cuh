@@ -27,6 +27,11 @@ int check_cuda(cudaError_t e, const char* what);
         if (!(cond)) { dtb::set_error(__VA_ARGS__); return dtb::DTB_EINVAL; } \
     } while (0)
 
+// ---- optional per-kernel CUDA-event timing (bench.py roofline leg; off by default, never on under graph capture) ----
+enum ProfTag { PROF_ENERGIES_FWD = 0, PROF_ENERGIES_BWD, PROF_PIT_TET, PROF_NN_QUERY, PROF_PFD_FORWARD, PROF_BARY_BWD, PROF_NTAGS };
+void prof_begin(int tag, cudaStream_t st);
+void prof_end(int tag, cudaStream_t st);
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -420,8 +420,10 @@ static int energies_forward_impl(const float* pos, const float* soup, const int3
                                                                     stats + (size_t)b0 * 8);
         } else {
             IndexedSrc s{pos + (size_t)b0 * V * 3, V};
+            prof_begin(PROF_ENERGIES_FWD, st);
             energies_fwd_kernel<IndexedSrc><<<tiles, E_TILE, 0, st>>>(s, tet, inv_v, nb, T, flags, vol ? vol + (size_t)b0 * T : nullptr,
                                                                        stats + (size_t)b0 * 8);
+            prof_end(PROF_ENERGIES_FWD, st);
         }
         DTB_LAUNCH_CHECK("energies_fwd");
     }
@@ -460,8 +462,10 @@ extern "C" int dtb_tet_energies_backward(const float* pos, const int32_t* tet, c
     int tiles = cdiv(T, E_TILE);
     IndexedSrc s{pos, V};
     ScatterDst d{grad_pos, V};
+    prof_begin(PROF_ENERGIES_BWD, st);
     energies_bwd_kernel<IndexedSrc, ScatterDst><<<tiles, E_TILE, 0, st>>>(s, d, tet, inv_v, B, T, flags, stats, g_amips, g_edge, g_volvar);
     DTB_LAUNCH_CHECK("energies_bwd");
+    prof_end(PROF_ENERGIES_BWD, st);
     return DTB_OK;
 }
 

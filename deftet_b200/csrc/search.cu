@@ -396,8 +396,10 @@ static int point_in_tet_impl(Src src, const float* points, int B, int T, int P, 
     DTB_CUDA(cudaMemsetAsync(hit, 0x7f, (size_t)B * P * sizeof(int), st));    // 0x7f7f7f7f: larger than any tet id
     if (T > 0) {
         dim3 grid(cdiv(T, 128), B);
+        prof_begin(PROF_PIT_TET, st);
         pit_tet_kernel<Src><<<grid, 128, 0, st>>>(src, T, P, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, hit);
         DTB_LAUNCH_CHECK("pit_tet");
+        prof_end(PROF_PIT_TET, st);
     }
     dim3 gf(cdiv(P, 256), B);
     pit_finalize_kernel<Src><<<gf, 256, 0, st>>>(src, points, P, hit, cond, bary);
@@ -428,8 +430,10 @@ extern "C" int dtb_tet_barycentric_backward(const float* pos, const int32_t* tet
     DTB_REQUIRE(pos && tet && points && cond && g_w, "tet_barycentric_backward: null argument");
     if (P == 0 || B == 0) return DTB_OK;
     dim3 grid(cdiv(P, 256), B);
+    prof_begin(PROF_BARY_BWD, (cudaStream_t)stream);
     bary_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pos, tet, V, points, P, cond, g_w, grad_pos, grad_points);
     DTB_LAUNCH_CHECK("bary_backward");
+    prof_end(PROF_BARY_BWD, (cudaStream_t)stream);
     return DTB_OK;
 }
 
@@ -483,9 +487,11 @@ static int nearest_neighbor_impl(const float* queries, const float* points, int3
     nn_qbin_fill_kernel<<<gq, 256, 0, st>>>(queries, Q, qcell, qend, qsorted);
     DTB_LAUNCH_CHECK("nn_qbin_fill");
     dim3 grid(cdiv(Q, 128), B);
+    prof_begin(PROF_NN_QUERY, st);
     nn_query_thread_kernel<<<grid, 128, 0, st>>>(queries, Q, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask, qsorted, qstart, qend,
                                                  q_counts, q_mult, result);
     DTB_LAUNCH_CHECK("nn_query_thread_sorted");
+    prof_end(PROF_NN_QUERY, st);
     return DTB_OK;
 }
 

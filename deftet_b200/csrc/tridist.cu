@@ -585,10 +585,12 @@ extern "C" int dtb_point_face_distance_forward(const float* points, const float*
     }
     const int NB = G / 4;
     dim3 grid(NB * NB * NB, B);
+    prof_begin(PROF_PFD_FORWARD, st);
     pfd_forward_tiled_kernel<<<grid, PFD_THREADS, 0, st>>>(S, faces, counts, Fmax, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted,
                                                            pg.mask, rmax, always, n_always, PFD_ALWAYS_CAP, qstart, qend, qsorted,
                                                            closest_d, closest_f);
     DTB_LAUNCH_CHECK("pfd_forward_tiled");
+    prof_end(PROF_PFD_FORWARD, st);
     return DTB_OK;
 }
 

@@ -37,6 +37,10 @@ extern "C" {
 const char* dtb_last_error(void);
 int dtb_version(void);                 /* 100 * major + minor */
 int dtb_device_is_sm100(int device);   /* 1 if the device is compute capability 10.x, 0 if not, <0 on error */
+/* Per-kernel CUDA-event timing for benchmarks (off by default; do not enable under CUDA-graph capture).  Tags:
+ * 0 energies_fwd, 1 energies_bwd, 2 pit_tet, 3 nn_query, 4 pfd_forward, 5 bary_backward.  elapsed() synchronises. */
+int dtb_profile_enable(int on);
+int dtb_profile_elapsed(int tag, float* ms);
 
 /* ---- A6/A7/A8: per-tet energies -------------------------------------------------------------------
  * Replaces DefTet.amips_energy / volume_variance / edge_length + autograd
