@@ -69,10 +69,10 @@ class Step:
         self.wvec = torch.tensor([w["amips"], w["edge"], w["volume_variance"], w["chamfer"], w["distance"], w["normal"], w["occupancy"]],
                                  device=engine.device).unsqueeze(-1)
 
-    def forward_backward(self, sc, u, v):
+    def forward_backward(self, sc, u, v, concurrent=True):
         eng = self.eng
         pos = sc["pos"] + self.delta.unsqueeze(0)
-        out = eng.losses(pos, sc["occ"], sc["gt"], u, v, sc["pts"])
+        out = eng.losses(pos, sc["occ"], sc["gt"], u, v, sc["pts"], concurrent=concurrent)
         cond, bary = out["condition"], out["barycentric"]
         pred = search.tet_interpolate(sc["vfield"].unsqueeze(-1), eng.tet, cond, bary).squeeze(-1)
         occ_loss = search.located_mse(pred, sc["target"], cond)
@@ -478,7 +478,7 @@ def roofline_pass(eng, step, scenes, uv, B, T, V, P, S, Fmax, S_face, NSETS, ite
     L.dtb_profile_enable(1)
     for k in range(6):
         step.delta.grad = None
-        step.forward_backward(scenes[k % NSETS], *uv[k % NSETS])
+        step.forward_backward(scenes[k % NSETS], *uv[k % NSETS], concurrent=False)     # serial: kernels timed in isolation
         torch.cuda.synchronize()
         if k >= 2:
             for ti, t in enumerate(tags):

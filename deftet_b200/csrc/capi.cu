@@ -19,8 +19,9 @@ int check_cuda(cudaError_t e, const char* what) {
 }
 
 struct ProfSlot { cudaEvent_t a = nullptr, b = nullptr; bool recorded = false; };
-static thread_local ProfSlot g_prof[PROF_NTAGS];
-static thread_local int g_prof_on = 0;
+// process-wide on purpose: autograd runs backward kernels from its own thread
+static ProfSlot g_prof[PROF_NTAGS];
+static volatile int g_prof_on = 0;
 void prof_begin(int tag, cudaStream_t st) {
     if (!g_prof_on) return;
     ProfSlot& p = g_prof[tag];
