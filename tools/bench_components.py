@@ -1,0 +1,126 @@
+"""Per-row measurements of the SURVEY.md section 8 scope table at the BASELINE.json configs (one JSON line per row).
+
+  python tools/bench_components.py [--quick] > profiles/components_rNN.jsonl     (on the B200 box)
+
+GPU numbers: CUDA events around the public call, median of repeated runs, L2 flushed between runs.  CPU numbers:
+the reference's own compiled builders (oracle/_ref, kind "reference") where they exist, else the oracle port."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+from deftet_b200 import builders, energies, render, search, surface
+from deftet_b200.grid import acute_lattice_grid
+from tools.quick_time import timeit
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    from oracle import native
+
+    # ---- config 2: res 40, batch 8, energies fwd+bwd (A6-A8) ------------------------------------------------------
+    for res, B in ((40, 8), (70, 8), (100, 4)):
+        g = acute_lattice_grid(res)
+        V, T = g.n_vert, g.n_tet
+        pos = torch.from_numpy(g.centred()).to(dev).unsqueeze(0).repeat(B, 1, 1)
+        pos = (pos + 0.1 / res * (torch.rand_like(pos) - 0.5)).requires_grad_(True)
+        tet = torch.from_numpy(g.tets).to(dev).to(torch.int32)
+        inv = energies.tet_inverse_v(torch.from_numpy(g.centred()).to(dev), tet)
+
+        def fb():
+            pos.grad = None
+            am, ed, vv = energies.tet_energies(pos, tet, inv)
+            (am + ed + vv).sum().backward()
+        med, _ = timeit(fb, 20, 3, flush)
+        by = 2 * 52 * T + 36 * B * V + 8 * B * T
+        emit(row="A6-A8 energies fwd+bwd", res=res, batch=B, V=V, T=T, ms=med, tets_per_ms=B * T / med, algorithmic_bytes=by,
+             hbm_frac=by / (med * 1e-3) / 1e9 / peak)
+
+        # ---- builders A10-A14 (config 4 = res 100, rebuilt every step) ---------------------------------------------
+        if res in (40, 100) or not a.quick:
+            rows = {"A10 tet_point_adj": lambda: builders.tet_point_adj(tet, V), "A11 tet_to_face": lambda: builders.tet_to_face(V, tet),
+                    "A12 tet_adj_share": lambda: builders.tet_adj_share(tet, V), "A13 tet_face_adj": lambda: builders.tet_face_adj(tet, V)}
+            soup = torch.from_numpy(g.centred()[g.tets.reshape(-1)]).to(dev)
+            rows["A14 collapse_vertices"] = lambda: builders.collapse_vertices(soup)
+            for name, fn in rows.items():
+                med, _ = timeit(fn, 5, 2, flush)
+                cpu = None
+                refname = {"A10": "tet_point_adj", "A12": "tet_adj_share", "A13": "tet_face_adj"}.get(name[:3])
+                try:
+                    if refname and native.ref_lib(refname) and (res <= 70 or name[:3] != "A13"):
+                        cols = {"tet_point_adj": (12, 2), "tet_adj_share": (8, 3), "tet_face_adj": (200, 2)}[refname]
+                        t0 = time.perf_counter()
+                        native.ref_run_tet_builder(refname, g.tets, V, T * cols[0], cols[1])
+                        cpu = {"ms": (time.perf_counter() - t0) * 1e3, "kind": "reference (utils/lib/%s/run.cpp, 1 thread, incl. file I/O of the out-of-process driver)" % refname}
+                    elif name[:3] == "A14" and native.ref_lib("colaps_v"):
+                        t0 = time.perf_counter()
+                        native.ref_colaps_v(soup.cpu().numpy())
+                        cpu = {"ms": (time.perf_counter() - t0) * 1e3, "kind": "reference (utils/lib/colaps_v/run.cpp, 1 thread)"}
+                except Exception as e:  # pragma: no cover
+                    cpu = {"error": str(e)[:100]}
+                emit(row=name, res=res, V=V, T=T, ms=med, tets_per_ms=T / med, cpu=cpu)
+
+    # ---- A1 alone at res 70 ---------------------------------------------------------------------------------------------
+    g = acute_lattice_grid(70)
+    B, P = 8, 100000
+    pos = torch.from_numpy(g.centred()).to(dev).unsqueeze(0).repeat(B, 1, 1)
+    tet = torch.from_numpy(g.tets).to(dev).to(torch.int32)
+    pts = (torch.rand(B, P, 3, device=dev) - 0.5) * 1.05
+    med, _ = timeit(lambda: search.point_in_tet(pos, tet, pts), 10, 3, flush)
+    by = B * 32 * P + 12 * B * g.n_vert + 16 * g.n_tet
+    emit(row="A1 point_in_tet fwd (+bary)", res=70, batch=B, points=P, ms=med, tets_per_ms=B * g.n_tet / med, algorithmic_bytes=by,
+         hbm_frac=by / (med * 1e-3) / 1e9 / peak)
+    soup_t = pos[:, tet.long().reshape(-1)].reshape(B, -1, 4, 3).contiguous()
+    med, _ = timeit(lambda: search.point_in_tet_soup(soup_t, pts), 10, 3, flush)
+    emit(row="A1 check_condition_f_base drop-in (materialised tet_bxfx4x3)", res=70, batch=B, points=P, ms=med, tets_per_ms=B * g.n_tet / med)
+
+    # ---- A15 rasterizer: config 5 scale (res-40 grid faces, 800x800 pixels, K=300) ---------------------------------------
+    g40 = acute_lattice_grid(40)
+    f3, ft2, fs2, bnd = builders.tet_to_face(g40.n_vert, torch.from_numpy(g40.tets).to(dev))
+    faces = torch.cat([f3, bnd]).long()
+    F = faces.shape[0]
+    vpos = torch.from_numpy(g40.centred()).to(dev) * 2.5
+    W = 400 if a.quick else 800
+    focal = 0.5 * W / np.tan(0.5 * 0.6911)
+    cam = vpos + torch.tensor([0.0, 0.0, -4.0], device=dev)
+    xy = cam[:, :2] / (-cam[:, 2:3]) * focal / (0.5 * W)
+    fz = cam[faces][..., 2].unsqueeze(0).contiguous()
+    fxy = (xy[faces] * 1000).unsqueeze(0).contiguous()
+    feat = torch.rand(1, F, 3, 4, device=dev)
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, W, device=dev), torch.linspace(-1, 1, W, device=dev), indexing="ij")
+    pix = (torch.stack([xs, ys], -1).reshape(1, -1, 2) * 1000).contiguous()
+    rng = torch.tensor([-1000.0, 0.0], device=dev).reshape(1, 1, 2).expand(1, pix.shape[1], 2).contiguous()
+    for K in ((64,) if a.quick else (64, 300)):
+        out, idx = render.deftet_sparse_render(pix, rng, fz, fxy, feat, knum=K)
+        hits = int((idx >= 0).sum())
+        med, _ = timeit(lambda: render.deftet_sparse_render(pix, rng, fz, fxy, feat, knum=K), 3, 1, flush)
+        by = pix.shape[1] * K * (16 + 8) + F * (12 + 24 + 48)
+        emit(row="A15 deftet_sparse_render fwd", pixels=pix.shape[1], faces=F, K=K, hits_per_pixel=hits / pix.shape[1], ms=med, algorithmic_bytes=by,
+             hbm_frac=by / (med * 1e-3) / 1e9 / peak, max_slots_used=int((idx >= 0).sum(-1).max()))
+        del out, idx
+    # ---- A16 check_sign: sphere mesh, T centroids -----------------------------------------------------------------------------
+    from tests.test_gpu_render import _icosphere
+    v, f = _icosphere(5)
+    verts = torch.from_numpy(v * 0.3).to(dev).unsqueeze(0)
+    cen = pos[:1, tet.long().reshape(-1)].reshape(1, -1, 4, 3).mean(2).contiguous()
+    med, _ = timeit(lambda: render.check_sign(verts, torch.from_numpy(f).to(dev), cen), 5, 2, flush)
+    emit(row="A16 check_sign", mesh_faces=int(f.shape[0]), points=int(cen.shape[1]), ms=med, tets_per_ms=cen.shape[1] / med)
+
+
+if __name__ == "__main__":
+    main()
