@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--points", type=int, default=100000)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="enqueue the loss groups on one stream (profiling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -245,7 +246,7 @@ def main():
 
     def run_eager(s):
         step.delta.grad = None
-        return step.forward_backward(scenes[s], *uv[s])
+        return step.forward_backward(scenes[s], *uv[s], concurrent=not args.serial)
 
     # warm-up (also JIT/allocator warm-up) on a side stream as graph capture requires
     side = torch.cuda.Stream()
@@ -264,7 +265,7 @@ def main():
                 g = torch.cuda.CUDAGraph()
                 step.delta.grad = None
                 with torch.cuda.graph(g):
-                    l, _, _ = step.forward_backward(scenes[s], *uv[s])
+                    l, _, _ = step.forward_backward(scenes[s], *uv[s], concurrent=not args.serial)
                 graphs.append((g, l, step.delta.grad))
             torch.cuda.synchronize()
         except Exception as e:  # pragma: no cover
