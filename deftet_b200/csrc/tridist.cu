@@ -87,15 +87,81 @@ __device__ __forceinline__ float tri_distance(const float* a, const float* b, co
     return xadd(h.plane2, h.inplane);
 }
 
+// Query-independent part of cuda_min_triangle_distance / cuda_line_distance, hoisted out of the per-query loop.
+// Every value is produced by the same operation sequence as in tri_distance(), so results stay bit-identical.
+struct FacePre {
+    float a[3], b[3], c[3];
+    float n[3];          // unit normal
+    float na;            // dot(n, a)
+    float k3;
+    float bc1, cb0, ac0, ca1;        // (b1-c1), (c0-b0), (a0-c0), (c1-a1)
+    float ab[3], bcv[3], ac[3];      // edge vectors B-A for the three edges (a,b), (b,c), (a,c)
+    float den_ab, den_bc, den_ac;    // div_nz(dot(BA,BA))
+    float pad[2];                    // 32 floats = 8 x float4
+};
+constexpr int FACEPRE_FLOATS = sizeof(FacePre) / 4;
+
+__device__ __forceinline__ void face_precompute(const float* t, FacePre& f) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { f.a[k] = t[k]; f.b[k] = t[3 + k]; f.c[k] = t[6 + k]; }
+    float r1[3] = {xsub(f.b[0], f.a[0]), xsub(f.b[1], f.a[1]), xsub(f.b[2], f.a[2])};
+    float r2[3] = {xsub(f.c[0], f.a[0]), xsub(f.c[1], f.a[1]), xsub(f.c[2], f.a[2])};
+    float n[3] = {xsub(xmul(r1[1], r2[2]), xmul(r1[2], r2[1])), xsub(xmul(r1[2], r2[0]), xmul(r1[0], r2[2])),
+                  xsub(xmul(r1[0], r2[1]), xmul(r1[1], r2[0]))};
+    float len = div_nz(xsqrt(xadd(xadd(xmul(n[0], n[0]), xmul(n[1], n[1])), xmul(n[2], n[2]))));
+    f.n[0] = xdiv(n[0], len); f.n[1] = xdiv(n[1], len); f.n[2] = xdiv(n[2], len);
+    f.na = xdot(f.n, f.a);
+    f.bc1 = xsub(f.b[1], f.c[1]); f.cb0 = xsub(f.c[0], f.b[0]); f.ac0 = xsub(f.a[0], f.c[0]); f.ca1 = xsub(f.c[1], f.a[1]);
+    f.k3 = xadd(xmul(f.bc1, f.ac0), xmul(f.cb0, xsub(f.a[1], f.c[1])));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { f.ab[k] = xsub(f.b[k], f.a[k]); f.bcv[k] = xsub(f.c[k], f.b[k]); f.ac[k] = xsub(f.c[k], f.a[k]); }
+    f.den_ab = div_nz(xdot(f.ab, f.ab)); f.den_bc = div_nz(xdot(f.bcv, f.bcv)); f.den_ac = div_nz(xdot(f.ac, f.ac));
+}
+__device__ __forceinline__ float line_dist2_pre(const float* A, const float* BA, float den, const float* P) {
+    float PA[3] = {xsub(P[0], A[0]), xsub(P[1], A[1]), xsub(P[2], A[2])};
+    float t = xdiv(xdot(PA, BA), den);
+    float d[3] = {xsub(PA[0], xmul(BA[0], t)), xsub(PA[1], xmul(BA[1], t)), xsub(PA[2], xmul(BA[2], t))};
+    float dist = xdot(d, d);
+    return (t >= 0.f && t <= 1.f) ? dist : -dist;
+}
+// forward-only distance (same value as tri_distance(..., FWD_MAX_DIS, ...))
+__device__ __forceinline__ float tri_distance_pre(const FacePre& f, const float* p) {
+    float t = xsub(f.na, xdot(f.n, p));
+    float ip[3] = {xadd(p[0], xmul(f.n[0], t)), xadd(p[1], xmul(f.n[1], t)), xadd(p[2], xmul(f.n[2], t))};
+    float plane2 = xmul(t, t);
+    if (f.k3 == 0.f) return FWD_MAX_DIS;
+    float ipc0 = xsub(ip[0], f.c[0]), ipc1 = xsub(ip[1], f.c[1]);
+    float k1 = xadd(xmul(f.bc1, ipc0), xmul(f.cb0, ipc1));
+    float k2 = xadd(xmul(f.ac0, ipc1), xmul(f.ca1, ipc0));
+    float l1 = xdiv(k1, f.k3), l2 = xdiv(k2, f.k3), l3 = xsub(xsub(1.0f, l1), l2);
+    if (l1 >= 0.f && l2 >= 0.f && l3 >= 0.f) return plane2;
+    float d12 = line_dist2_pre(f.a, f.ab, f.den_ab, ip), d23 = line_dist2_pre(f.b, f.bcv, f.den_bc, ip), d13 = line_dist2_pre(f.a, f.ac, f.den_ac, ip);
+    if (d12 <= 0.f) d12 = FWD_MAX_DIS;
+    if (d23 <= 0.f) d23 = FWD_MAX_DIS;
+    if (d13 <= 0.f) d13 = FWD_MAX_DIS;
+    float ml = xmin3(d12, d23, d13);
+    float mp = xmin3(pt_dist2(f.a, ip), pt_dist2(f.b, ip), pt_dist2(f.c, ip));
+    return xadd(plane2, (ml < mp) ? ml : mp);
+}
+
 // ---- per-sample face statistics: R_max and the "always test" list ---------------------------------------
 __global__ void __launch_bounds__(256) face_stats_kernel(const float* __restrict__ soup, const int32_t* __restrict__ counts, int Fmax,
                                                          unsigned* __restrict__ rmax_bits, int32_t* __restrict__ always,
-                                                         int32_t* __restrict__ n_always, int always_cap) {
+                                                         int32_t* __restrict__ n_always, int always_cap, float4* __restrict__ pre) {
     int b = blockIdx.y;
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     float r = 0.f;
     if (f < counts[b]) {
         const float* t = soup + ((size_t)b * Fmax + f) * 9;
+        if (pre) {                                   // query-independent half of the distance, once per face
+            FacePre fp;
+            face_precompute(t, fp);
+            fp.pad[0] = fp.pad[1] = 0.f;
+            const float4* src = reinterpret_cast<const float4*>(&fp);
+            float4* dst = pre + ((size_t)b * Fmax + f) * 8;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) dst[m] = src[m];
+        }
         float cx = (t[0] + t[3] + t[6]) * (1.f / 3.f), cy = (t[1] + t[4] + t[7]) * (1.f / 3.f), cz = (t[2] + t[5] + t[8]) * (1.f / 3.f);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -164,62 +230,6 @@ __global__ void __launch_bounds__(256) qbin_fill_kernel(const float* __restrict_
     qsorted[dst] = make_float4(p[0], p[1], p[2], __int_as_float(i));
 }
 
-// Query-independent part of cuda_min_triangle_distance / cuda_line_distance, hoisted out of the per-query loop.
-// Every value is produced by the same operation sequence as in tri_distance(), so results stay bit-identical.
-struct FacePre {
-    float a[3], b[3], c[3];
-    float n[3];          // unit normal
-    float na;            // dot(n, a)
-    float k3;
-    float bc1, cb0, ac0, ca1;        // (b1-c1), (c0-b0), (a0-c0), (c1-a1)
-    float ab[3], bcv[3], ac[3];      // edge vectors B-A for the three edges (a,b), (b,c), (a,c)
-    float den_ab, den_bc, den_ac;    // div_nz(dot(BA,BA))
-};
-constexpr int FACEPRE_FLOATS = sizeof(FacePre) / 4;
-
-__device__ __forceinline__ void face_precompute(const float* t, FacePre& f) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { f.a[k] = t[k]; f.b[k] = t[3 + k]; f.c[k] = t[6 + k]; }
-    float r1[3] = {xsub(f.b[0], f.a[0]), xsub(f.b[1], f.a[1]), xsub(f.b[2], f.a[2])};
-    float r2[3] = {xsub(f.c[0], f.a[0]), xsub(f.c[1], f.a[1]), xsub(f.c[2], f.a[2])};
-    float n[3] = {xsub(xmul(r1[1], r2[2]), xmul(r1[2], r2[1])), xsub(xmul(r1[2], r2[0]), xmul(r1[0], r2[2])),
-                  xsub(xmul(r1[0], r2[1]), xmul(r1[1], r2[0]))};
-    float len = div_nz(xsqrt(xadd(xadd(xmul(n[0], n[0]), xmul(n[1], n[1])), xmul(n[2], n[2]))));
-    f.n[0] = xdiv(n[0], len); f.n[1] = xdiv(n[1], len); f.n[2] = xdiv(n[2], len);
-    f.na = xdot(f.n, f.a);
-    f.bc1 = xsub(f.b[1], f.c[1]); f.cb0 = xsub(f.c[0], f.b[0]); f.ac0 = xsub(f.a[0], f.c[0]); f.ca1 = xsub(f.c[1], f.a[1]);
-    f.k3 = xadd(xmul(f.bc1, f.ac0), xmul(f.cb0, xsub(f.a[1], f.c[1])));
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { f.ab[k] = xsub(f.b[k], f.a[k]); f.bcv[k] = xsub(f.c[k], f.b[k]); f.ac[k] = xsub(f.c[k], f.a[k]); }
-    f.den_ab = div_nz(xdot(f.ab, f.ab)); f.den_bc = div_nz(xdot(f.bcv, f.bcv)); f.den_ac = div_nz(xdot(f.ac, f.ac));
-}
-__device__ __forceinline__ float line_dist2_pre(const float* A, const float* BA, float den, const float* P) {
-    float PA[3] = {xsub(P[0], A[0]), xsub(P[1], A[1]), xsub(P[2], A[2])};
-    float t = xdiv(xdot(PA, BA), den);
-    float d[3] = {xsub(PA[0], xmul(BA[0], t)), xsub(PA[1], xmul(BA[1], t)), xsub(PA[2], xmul(BA[2], t))};
-    float dist = xdot(d, d);
-    return (t >= 0.f && t <= 1.f) ? dist : -dist;
-}
-// forward-only distance (same value as tri_distance(..., FWD_MAX_DIS, ...))
-__device__ __forceinline__ float tri_distance_pre(const FacePre& f, const float* p) {
-    float t = xsub(f.na, xdot(f.n, p));
-    float ip[3] = {xadd(p[0], xmul(f.n[0], t)), xadd(p[1], xmul(f.n[1], t)), xadd(p[2], xmul(f.n[2], t))};
-    float plane2 = xmul(t, t);
-    if (f.k3 == 0.f) return FWD_MAX_DIS;
-    float ipc0 = xsub(ip[0], f.c[0]), ipc1 = xsub(ip[1], f.c[1]);
-    float k1 = xadd(xmul(f.bc1, ipc0), xmul(f.cb0, ipc1));
-    float k2 = xadd(xmul(f.ac0, ipc1), xmul(f.ca1, ipc0));
-    float l1 = xdiv(k1, f.k3), l2 = xdiv(k2, f.k3), l3 = xsub(xsub(1.0f, l1), l2);
-    if (l1 >= 0.f && l2 >= 0.f && l3 >= 0.f) return plane2;
-    float d12 = line_dist2_pre(f.a, f.ab, f.den_ab, ip), d23 = line_dist2_pre(f.b, f.bcv, f.den_bc, ip), d13 = line_dist2_pre(f.a, f.ac, f.den_ac, ip);
-    if (d12 <= 0.f) d12 = FWD_MAX_DIS;
-    if (d23 <= 0.f) d23 = FWD_MAX_DIS;
-    if (d13 <= 0.f) d13 = FWD_MAX_DIS;
-    float ml = xmin3(d12, d23, d13);
-    float mp = xmin3(pt_dist2(f.a, ip), pt_dist2(f.b, ip), pt_dist2(f.c, ip));
-    return xadd(plane2, (ml < mp) ? ml : mp);
-}
-
 // One CTA per brick of queries: the faces binned in the 3x3x3 surrounding bricks are staged once in shared
 // memory (centroid + the query-independent half of the distance computation) and every query of the brick
 //   1. finds the candidate with the nearest centroid and evaluates it (all lanes together: no divergence, and the
@@ -235,20 +245,29 @@ constexpr int PFD_CHUNK = 128;      // staged candidate capacity (< 256: survivo
 constexpr int PFD_SCAN = 128;       // candidates of the 27 bricks inspected per staging round (<= PFD_CHUNK)
 constexpr int PFD_LIST = 12;        // survivors remembered per query and chunk
 
+__device__ __forceinline__ unsigned long long pack_df(float d, int f) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)f; }
+
 __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_kernel(
-    int S, const float* __restrict__ soup, const int32_t* __restrict__ counts, int Fmax, int G, const unsigned* __restrict__ bbox_ord,
-    const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end, const float4* __restrict__ sorted,
-    const unsigned long long* __restrict__ mask, const unsigned* __restrict__ rmax_bits, const int32_t* __restrict__ always,
-    const int32_t* __restrict__ n_always, int always_cap, const unsigned* __restrict__ qstart, const unsigned* __restrict__ qend,
-    const float4* __restrict__ qsorted, float* __restrict__ closest_d, float* __restrict__ closest_f) {
+    int S, const float* __restrict__ soup, const float4* __restrict__ pre, const int32_t* __restrict__ counts, int Fmax, int G,
+    const unsigned* __restrict__ bbox_ord, const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
+    const float4* __restrict__ sorted, const unsigned long long* __restrict__ mask, const unsigned* __restrict__ rmax_bits,
+    const int32_t* __restrict__ always, const int32_t* __restrict__ n_always, int always_cap, const unsigned* __restrict__ qstart,
+    const unsigned* __restrict__ qend, const float4* __restrict__ qsorted, float* __restrict__ closest_d, float* __restrict__ closest_f) {
+    constexpr int WARPS = PFD_THREADS / 32;
     __shared__ float4 s_cen[PFD_CHUNK];
-    __shared__ float s_pre[PFD_CHUNK * FACEPRE_FLOATS];
+    __shared__ __align__(16) float s_pre[PFD_CHUNK * FACEPRE_FLOATS];
     __shared__ unsigned s_rs[27], s_re[27];
     __shared__ unsigned s_total;
+    __shared__ unsigned s_n;
+    __shared__ unsigned char s_rel[PFD_CHUNK];        // 1 = the centroid distance is a valid upper bound for this face
     __shared__ unsigned char s_list[PFD_THREADS][PFD_LIST];
+    __shared__ float s_q[WARPS][32][3];               // the warp's queries (pooled evaluation reads other lanes' queries)
+    __shared__ unsigned long long s_best[WARPS][32];  // (distance bits, face id): atomicMin == lexicographic minimum
+    __shared__ unsigned short s_pairs[WARPS][32 * PFD_LIST];
     const int b = blockIdx.y;
     const int NB = G >> 2;
     const int brick = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t qb = (size_t)b * NB * NB * NB + brick;
     const unsigned q0 = qstart[qb], q1 = qend[qb];
     if (q0 == q1) return;
@@ -257,6 +276,7 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
     const int bz0 = brick / (NB * NB), by0 = (brick / NB) % NB, bx0 = brick % NB;
     const size_t cell_base = (size_t)b * G * G * G;
     const float* sb = soup + (size_t)b * Fmax * 9;
+    const float4* preb = pre + (size_t)b * Fmax * 8;
     const GridParams g = grid_params(bbox_ord, b, G);
     const float rmax = __uint_as_float(rmax_bits[b]) * 1.001f + 1e-7f;
     const bool brute = na > always_cap;
@@ -288,8 +308,6 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
     const float lx0 = g.ox + (float)bx0 * bw, ly0 = g.oy + (float)by0 * bw, lz0 = g.oz + (float)bz0 * bw;
     const float rlo[3] = {lx0 - reach, ly0 - reach, lz0 - reach}, rhi[3] = {lx0 + bw + reach, ly0 + bw + reach, lz0 + bw + reach};
     const float gmax = (float)G * g.h;
-    __shared__ unsigned s_n;
-    __shared__ unsigned char s_rel[PFD_CHUNK];      // 1 = the centroid distance is a valid upper bound for this face
     for (unsigned qbase = q0; qbase < q1; qbase += PFD_THREADS) {
         const unsigned qi = qbase + threadIdx.x;
         const bool active = qi < q1;
@@ -303,6 +321,7 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
             if (brute) { for (int f = 0; f < nf; ++f) v.face(f); }
             else { for (int k = 0; k < na; ++k) v.face(always[(size_t)b * always_cap + k]); }
         } else { v.p[0] = v.p[1] = v.p[2] = 0.f; }
+        s_q[warp][lane][0] = v.p[0]; s_q[warp][lane][1] = v.p[1]; s_q[warp][lane][2] = v.p[2];
         float ub = 3.0e38f;                                 // upper bound of the answer: a centroid is a point of its face
         for (unsigned c0 = 0; c0 < total; c0 += PFD_SCAN) {
             // ---- stage (compacting): candidates c0 .. c0+PFD_SCAN of the 27 bricks that lie in the reach region ----
@@ -321,17 +340,16 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
                 }
                 unsigned bal = __ballot_sync(0xffffffffu, keep);
                 unsigned base = 0;
-                if ((threadIdx.x & 31) == 0 && bal) base = atomicAdd(&s_n, (unsigned)__popc(bal));
+                if (lane == 0 && bal) base = atomicAdd(&s_n, (unsigned)__popc(bal));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (keep) {
-                    unsigned k = base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+                    unsigned k = base + __popc(bal & ((1u << lane) - 1u));
                     s_cen[k] = it;
-                    FacePre fp;
-                    face_precompute(sb + (size_t)__float_as_int(it.w) * 9, fp);
-                    float* dst = s_pre + (size_t)k * FACEPRE_FLOATS;
-                    const float* src = reinterpret_cast<const float*>(&fp);
+                    const float4* src = preb + (size_t)__float_as_int(it.w) * 8;
+                    float4* dst = reinterpret_cast<float4*>(s_pre + (size_t)k * FACEPRE_FLOATS);
 #pragma unroll
-                    for (int m = 0; m < FACEPRE_FLOATS; ++m) dst[m] = src[m];
+                    for (int m = 0; m < 8; ++m) dst[m] = __ldg(src + m);
+                    const FacePre& fp = *reinterpret_cast<const FacePre*>(dst);
                     // same reliability rule as face_stats_kernel (unit normal here): unreliable or invisible faces may
                     // have a reference distance larger than the distance to their centroid
                     s_rel[k] = (fp.k3 != 0.f && fabsf(fp.n[2]) > 2e-3f) ? 1 : 0;
@@ -339,20 +357,31 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
             }
             __syncthreads();
             const int n = (int)s_n;
-            // ---- scan 1: upper bound of the answer from the centroid distances (a centroid is a point of its face) ----
+            // ---- scan 1: upper bound from the centroid distances, and the nearest centroid ----
+            int kn = -1;
+            float dn = 3.0e38f;
             if (active) {
                 for (int k = 0; k < n; ++k) {
                     float4 it = s_cen[k];
                     float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
                     float d2 = dx * dx + dy * dy + dz * dz;
+                    if (d2 < dn) { dn = d2; kn = k; }
                     if (s_rel[k]) ub = fminf(ub, d2);
                 }
+            }
+            // the nearest-centroid face is evaluated by every lane at the same time (convergent): tight running minimum
+            if (kn >= 0) {
+                const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)kn * FACEPRE_FLOATS);
+                float d = tri_distance_pre(fp, v.p);
+                int f = __float_as_int(s_cen[kn].w);
+                if (v.best > d || (d == v.best && v.bi >= 0 && f < v.bi)) { v.best = d; v.bi = f; }
             }
             // ---- scan 2: remember the candidates the bounding sphere cannot reject against that bound ----
             int ns = 0;
             if (active) {
                 const float bound = fminf(ub * 1.0001f, v.best);
                 for (int k = 0; k < n; ++k) {
+                    if (k == kn) continue;
                     float4 it = s_cen[k];
                     float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
                     float lb = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz) - rmax, 0.f) * 0.9999f;
@@ -366,22 +395,34 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
                     }
                 }
             }
-            // ---- evaluate the j-th remembered candidate of every lane together (lanes stay converged on the long distance code);
-            //      latest entries first: they were admitted under the tightest bound ----
-            for (int j = PFD_LIST - 1; j >= 0; --j) {
-                if (!__any_sync(0xffffffffu, j < ns)) continue;
-                if (j < ns) {
-                    int k = s_list[threadIdx.x][j];
-                    float4 it = s_cen[k];
-                    float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
-                    float lb = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz) - rmax, 0.f) * 0.9999f;
-                    if (!(lb * lb > fminf(ub * 1.0001f, v.best))) {
-                        const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_FLOATS);
-                        float d = tri_distance_pre(fp, v.p);
-                        int f = __float_as_int(it.w);
-                        if (v.best > d || (d == v.best && v.bi >= 0 && f < v.bi)) { v.best = d; v.bi = f; }
-                    }
+            // ---- pooled evaluation: the (query, candidate) pairs of the whole warp are evaluated 32 at a time, whoever owns
+            //      them, and min-reduced per query with a 64-bit atomicMin on (distance bits, face id) ----
+            s_best[warp][lane] = pack_df(v.best, v.bi);
+            unsigned incl = (unsigned)ns;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            const unsigned tot_pairs = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned wofs = incl - (unsigned)ns;
+            for (int j = 0; j < ns; ++j) s_pairs[warp][wofs + j] = (unsigned short)((lane << 8) | s_list[threadIdx.x][j]);
+            __syncwarp();
+            for (unsigned p0 = 0; p0 < tot_pairs; p0 += 32) {
+                unsigned pi = p0 + lane;
+                if (pi < tot_pairs) {
+                    unsigned pr = s_pairs[warp][pi];
+                    int ql = (int)(pr >> 8), k = (int)(pr & 255u);
+                    float qp[3] = {s_q[warp][ql][0], s_q[warp][ql][1], s_q[warp][ql][2]};
+                    const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_FLOATS);
+                    float d = tri_distance_pre(fp, qp);
+                    // a face at MAX_DIS (invisible, k3 == 0) can never win the strict '<' against the initial 10000
+                    if (d < FWD_MAX_DIS) atomicMin(&s_best[warp][ql], pack_df(d, __float_as_int(s_cen[k].w)));
                 }
+            }
+            __syncwarp();
+            {
+                unsigned long long pb = s_best[warp][lane];
+                float d = __uint_as_float((unsigned)(pb >> 32));
+                int f = (int)(unsigned)(pb & 0xffffffffull);
+                if (active) { v.best = d; v.bi = f; }        // s_best only ever decreased from (v.best, v.bi)
             }
         }
         if (active && !brute && nf > 0) {
@@ -532,7 +573,8 @@ extern "C" size_t dtb_point_face_distance_workspace(int B, int S, int Fmax, int 
     G = (G + 3) / 4 * 4;
     size_t nbr = (size_t)B * (G / 4) * (G / 4) * (G / 4);
     return pointgrid_workspace_bytes(B, Fmax, G, true, true) + align_up((size_t)B * PFD_ALWAYS_CAP * 4, 256) + 1024 +
-           2 * align_up(nbr * 4, 256) + align_up((size_t)B * S * 4, 256) + align_up((size_t)B * S * 16, 256) + scan_workspace_bytes(nbr) + 256;
+           2 * align_up(nbr * 4, 256) + align_up((size_t)B * S * 4, 256) + align_up((size_t)B * S * 16, 256) + scan_workspace_bytes(nbr) + 256 +
+           align_up((size_t)B * Fmax * 128, 256);
 }
 
 // counts (B,) i32: number of valid faces of each sample (the reference passes it as float n_face_b).
@@ -563,6 +605,7 @@ extern "C" int dtb_point_face_distance_forward(const float* points, const float*
     float4* qsorted = ws.take<float4>((size_t)B * S);
     size_t qsb = scan_workspace_bytes(nbr);
     void* qsws = ws.take<char>(qsb);
+    float4* pre = ws.take<float4>((size_t)B * Fmax * 8);
     if (!ws.ok || !workspace) { set_error("point_face_distance: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return DTB_EWORKSPACE; }
     DTB_CUDA(cudaMemsetAsync(rmax, 0, B * sizeof(unsigned), st));
     DTB_CUDA(cudaMemsetAsync(n_always, 0, B * sizeof(int32_t), st));
@@ -570,7 +613,7 @@ extern "C" int dtb_point_face_distance_forward(const float* points, const float*
         int rc = pointgrid_build_ragged(pg, faces, true, counts, st);
         if (rc) return rc;
         dim3 gs(cdiv(Fmax, 256), B);
-        face_stats_kernel<<<gs, 256, 0, st>>>(faces, counts, Fmax, rmax, always, n_always, PFD_ALWAYS_CAP);
+        face_stats_kernel<<<gs, 256, 0, st>>>(faces, counts, Fmax, rmax, always, n_always, PFD_ALWAYS_CAP, pre);
         DTB_LAUNCH_CHECK("face_stats");
     }
     {
@@ -586,7 +629,7 @@ extern "C" int dtb_point_face_distance_forward(const float* points, const float*
     const int NB = G / 4;
     dim3 grid(NB * NB * NB, B);
     prof_begin(PROF_PFD_FORWARD, st);
-    pfd_forward_tiled_kernel<<<grid, PFD_THREADS, 0, st>>>(S, faces, counts, Fmax, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted,
+    pfd_forward_tiled_kernel<<<grid, PFD_THREADS, 0, st>>>(S, faces, pre, counts, Fmax, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted,
                                                            pg.mask, rmax, always, n_always, PFD_ALWAYS_CAP, qstart, qend, qsorted,
                                                            closest_d, closest_f);
     DTB_LAUNCH_CHECK("pfd_forward_tiled");
