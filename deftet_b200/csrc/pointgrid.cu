@@ -90,20 +90,6 @@ __global__ void pg_brick_mask_kernel(const unsigned* __restrict__ cell_start, co
     mask[w] = m;
 }
 
-__global__ void pg_mask_kernel(const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end, int G, int W,
-                               size_t n_words, unsigned long long* __restrict__ mask) {
-    size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_words) return;
-    size_t row = w / W;
-    int x0 = (int)(w % W) * 64;
-    unsigned long long m = 0;
-    for (int k = 0; k < 64 && x0 + k < G; ++k) {
-        size_t c = row * G + x0 + k;
-        if (cell_end[c] > cell_start[c]) m |= (1ull << k);
-    }
-    mask[w] = m;
-}
-
 size_t pointgrid_workspace_bytes(int B, int N, int G, bool with_mask, bool brick) {
     Workspace ws(nullptr, 0);
     PointGrid pg;
@@ -112,7 +98,7 @@ size_t pointgrid_workspace_bytes(int B, int N, int G, bool with_mask, bool brick
 }
 
 bool pointgrid_carve(PointGrid& pg, int B, int N, int G, bool with_mask, bool brick, Workspace& ws) {
-    pg.B = B; pg.N = N; pg.G = G; pg.W = (G + 63) / 64; pg.brick = brick;
+    pg.B = B; pg.N = N; pg.G = G; pg.brick = brick;
     size_t cells = (size_t)B * G * G * G;
     // bbox_ord and cell_start are adjacent (bbox padded to 256 B) so that one memset clears both
     pg.bbox_ord = ws.take<unsigned>((size_t)B * 6);
@@ -121,7 +107,7 @@ bool pointgrid_carve(PointGrid& pg, int B, int N, int G, bool with_mask, bool br
     pg.cell_end = ws.take<unsigned>(cells);
     pg.sorted = ws.take<float4>((size_t)B * N);
     pg.cell_of = ws.take<unsigned>((size_t)B * N);
-    pg.mask = with_mask ? ws.take<unsigned long long>(brick ? cells / 64 : (size_t)B * G * G * pg.W) : nullptr;
+    pg.mask = (with_mask && brick) ? ws.take<unsigned long long>(cells / 64) : nullptr;
     pg.scan_ws_bytes = scan_workspace_bytes(cells);
     pg.scan_ws = ws.take<char>(pg.scan_ws_bytes);
     return ws.ok;
@@ -157,9 +143,8 @@ int pointgrid_build_ragged(PointGrid& pg, const float* items, bool tri, const in
         pg_brick_mask_kernel<<<cdiv((long long)n_bricks, 128), 128, 0, st>>>(pg.cell_start, pg.cell_end, n_bricks, pg.mask);
         DTB_LAUNCH_CHECK("pg_brick_mask");
     } else if (pg.mask) {
-        size_t n_words = (size_t)B * G * G * pg.W;
-        pg_mask_kernel<<<cdiv((long long)n_words, 256), 256, 0, st>>>(pg.cell_start, pg.cell_end, G, pg.W, n_words, pg.mask);
-        DTB_LAUNCH_CHECK("pg_mask");
+        set_error("pointgrid: occupancy masks exist for the brick layout only");
+        return DTB_EINVAL;
     }
     return DTB_OK;
 }

@@ -5,8 +5,7 @@
 //   bbox_ord [B][6]            order-preserving-encoded min xyz / max xyz of the items
 //   cell_start/cell_end [B*G^3] item range of each cell inside `sorted`
 //   sorted  [B*N] float4       (x, y, z, original index as int bits), grouped by cell
-//   mask    u64 occupancy words, optional: row-major layout -> [B*G*G*W] bits along x (W = ceil(G/64));
-//           brick layout -> [B*(G/4)^3], bit (z&3)*16+(y&3)*4+(x&3) of the brick's word
+//   mask    [B*(G/4)^3] u64    brick layout only: bit (z&3)*16+(y&3)*4+(x&3) of the brick's word = cell occupied
 // Cell of x on one axis: clamp(floor((x - min) * inv_h), 0, G-1), inv_h = G / (max extent * (1 + 2^-20)):
 // monotone in x, so conservative cell ranges of boxes are obtained by mapping their corners.
 #pragma once
@@ -21,7 +20,7 @@ struct GridParams {     // per-sample, computed on device from bbox_ord
 };
 
 struct PointGrid {
-    int B, N, G, W;
+    int B, N, G;
     bool brick;               // cell order: false = row-major (z,y,x); true = 4x4x4 bricks (G % 4 == 0), 64 cells per brick
     unsigned* bbox_ord;       // [B][6]
     unsigned* cell_start;     // [B*G^3]

@@ -1,0 +1,105 @@
+"""Drop-in `DefTet` module (deftet_b200/deftet.py) end to end on the GPU: same call sequence as the reference's
+ParallelWrapper (parallel.py:199-214) on synthetic data, checked against the oracle restatement of
+DefTet.forward_surface_align (layers/DefTet/deftet.py:51-130); plus the thread-per-GPU calling pattern of nn.DataParallel."""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import builders as orc_b
+from oracle import energies as orc_e
+from oracle import native as orc
+from oracle import surface as orc_s
+from tests.test_gpu_render import _icosphere
+from tests.util import deformed_grid, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(res=10, B=2):
+    g, pos, tet = deformed_grid(res, B, seed=11)
+    v, f = _icosphere(3)
+    radii = [0.27, 0.33]
+    verts = [torch.from_numpy(v * r).float().unsqueeze(0) for r in radii[:B]]
+    faces = [torch.from_numpy(f).unsqueeze(0) for _ in range(B)]
+    f3, ft2, _, _ = orc_b.tet_to_face(g.n_vert, g.tets)
+    gen = torch.Generator().manual_seed(0)
+    d = torch.randn(B, 4000, 3, generator=gen)
+    gt = d / d.norm(dim=-1, keepdim=True) * torch.tensor(radii[:B]).reshape(B, 1, 1)
+    pts = (torch.rand(B, 3000, 3, generator=gen) - 0.5) * 1.05
+    return g, pos, tet, verts, faces, torch.from_numpy(f3), torch.from_numpy(ft2), gt, pts, v, f, radii
+
+
+def test_forward_surface_align_matches_oracle():
+    from deftet_b200.deftet import DefTet
+    g, pos, tet, verts, faces, f3, ft2, gt, pts, v, f, radii = _inputs()
+    B = pos.shape[0]
+    dev = torch.device("cuda")
+    net = DefTet()
+    net.inverse_v = net.tet_inverse_v(torch.from_numpy(g.centred()).to(dev), tet.to(dev))
+    dpos = pos.to(dev).requires_grad_(True)
+    mesh_list = [[x.to(dev) for x in verts], [x.to(dev) for x in faces]]
+    out = net.forward_surface_align(dpos, pts.to(dev), tetrahedron_bxfx4=tet.to(dev).unsqueeze(0).expand(B, -1, -1), mesh_list=mesh_list,
+                                    gt_surface_points=gt.to(dev), tet_face_bxfx3=f3.to(dev).unsqueeze(0).expand(B, -1, -1),
+                                    tet_face_tet_bx4fx2=ft2.to(dev).unsqueeze(0).expand(B, -1, -1), inference=True,
+                                    pred_occ=torch.rand(B, g.n_tet, device=dev))
+    (amips, edge, volvar, analytic, normal, center_occ, condition, boundary, pred_surface, chamfer) = out
+    # occupancy labels = oracle ray parity on the centroids
+    soup = orc_e.gather_tets(pos, tet)
+    ref_occ = np.stack([orc.check_sign(verts[b].numpy(), f, soup[b].mean(dim=1).unsqueeze(0).numpy())[0] for b in range(B)]).astype(np.float32)
+    assert np.array_equal(center_occ.cpu().numpy(), ref_occ)
+    ref_bnd = orc_s.get_boundary_index(f3, ft2, torch.from_numpy(ref_occ))
+    assert all(torch.equal(a.cpu(), r) for a, r in zip(boundary, ref_bnd))
+    # RNG-free losses against the per-sample oracle loop
+    inv = orc_e.tet_inverse_v(torch.from_numpy(g.centred()), tet)
+    assert rel_err(amips, orc_e.amips_energy(soup, inv)) < 1e-5
+    assert rel_err(edge, orc_e.edge_length(soup)) < 1e-5
+    u = [torch.sqrt(torch.rand(1, int(b.shape[0]), 20, 1)) for b in ref_bnd]
+    vv = [torch.rand(1, int(b.shape[0]), 20, 1) for b in ref_bnd]
+    ch, an, nl = orc_s.surface_losses(pos, ref_bnd, gt, u, vv)
+    assert rel_err(analytic, an.mean().reshape(1)) < 1e-5
+    assert rel_err(normal, nl.mean().reshape(1)) < 1e-5
+    assert abs(float(chamfer) - float(ch.mean())) < 0.05 * float(ch.mean())          # different random samples, same estimator
+    assert np.array_equal(condition.cpu().numpy(), orc.point_in_tet(soup.numpy(), pts.numpy()))
+    assert len(pred_surface) == B
+    (amips.mean() + edge.mean() + analytic.sum() + normal.sum() + chamfer.sum()).backward()
+    assert torch.isfinite(dpos.grad).all() and float(dpos.grad.abs().max()) > 0
+    # paste_occ keeps the reference quirk: misses are clamped to tet 0 (deftet.py:133)
+    occ_pts = net.paste_occ(torch.rand(B, g.n_tet, device=dev), condition.clone())
+    assert occ_pts.shape == (B, pts.shape[1])
+
+
+def test_thread_per_call_pattern_is_safe():
+    """nn.DataParallel drives one Python thread per replica; here two threads hammer the same library on different
+    streams and must reproduce the single-threaded results."""
+    from deftet_b200 import energies, search
+    g, pos, tet = deformed_grid(10, 2, seed=5)
+    dev = torch.device("cuda")
+    tet32 = tet.to(dev).to(torch.int32)
+    inv = energies.tet_inverse_v(torch.from_numpy(g.centred()).to(dev), tet32)
+    gen = torch.Generator().manual_seed(3)
+    pts = ((torch.rand(2, 4000, 3, generator=gen) - 0.5) * 1.05).to(dev)
+    dpos = pos.to(dev)
+    ref_c, ref_w = search.point_in_tet(dpos, tet32, pts)
+    ref_e = energies.tet_energies(dpos, tet32, inv)
+    torch.cuda.synchronize()
+    errors = []
+
+    def work(i):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(20):
+                    c, w = search.point_in_tet(dpos, tet32, pts)
+                    e = energies.tet_energies(dpos, tet32, inv)
+                s.synchronize()
+                assert torch.equal(c, ref_c) and torch.allclose(w, ref_w)
+                assert all(torch.allclose(a, b, rtol=1e-6) for a, b in zip(e, ref_e))
+        except Exception as ex:  # pragma: no cover
+            errors.append(ex)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(3)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors
