@@ -15,16 +15,17 @@ c_obj_tet_adj_share = Tet_adj_share()
 
 
 def scaler_triplet_produt(a, b, c):
-    return torch.sum(a * torch.cross(b, c, dim=-1), dim=-1)
+    return (a * torch.linalg.cross(b, c, dim=-1)).sum(dim=-1)
 
 
-def bary_centric_tet(a, b, c, d, p):          # utils/tet_utils.py:28-45 (pure torch in the reference too)
-    vap, vbp = p - a, p - b
-    vab, vac, vad = b - a, c - a, d - a
-    vbc, vbd = c - b, d - b
-    v6 = 1 / scaler_triplet_produt(vab, vac, vad)
-    return (scaler_triplet_produt(vbp, vbd, vbc) * v6, scaler_triplet_produt(vap, vac, vad) * v6,
-            scaler_triplet_produt(vap, vad, vab) * v6, scaler_triplet_produt(vap, vab, vac) * v6)
+def bary_centric_tet(a, b, c, d, p):
+    """Barycentric weights of p in tet (a,b,c,d) as ratios of signed volumes (reference utils/tet_utils.py:28-45)."""
+    inv6v = scaler_triplet_produt(b - a, c - a, d - a).reciprocal()
+    wa = scaler_triplet_produt(p - b, d - b, c - b)
+    wb = scaler_triplet_produt(p - a, c - a, d - a)
+    wc = scaler_triplet_produt(p - a, d - a, b - a)
+    wd = scaler_triplet_produt(p - a, b - a, c - a)
+    return wa * inv6v, wb * inv6v, wc * inv6v, wd * inv6v
 
 
 def c_tet_to_adj_sparse(points, tet_list, normalize=True):

@@ -310,3 +310,48 @@ class _NormalLoss(torch.autograd.Function):
 
 def surface_normal_loss(pos, faces, counts):
     return _NormalLoss.apply(pos, faces, counts)
+
+
+# ====================================================================================================
+# host-level mirrors of utils/mesh_utils.py (dense tensors in, same return conventions)
+# ====================================================================================================
+def face_unit_normals(corner_a, corner_b, corner_c):
+    """Unit normals with the reference's regulariser: cross / sqrt(|cross|^2 + 1e-12) (utils/mesh_utils.py:42-53)."""
+    cr = torch.linalg.cross(corner_b - corner_a, corner_c - corner_a, dim=-1)
+    return cr * torch.rsqrt((cr * cr).sum(dim=-1, keepdim=True) + 1e-12)
+
+
+def surface_normal_loss_dense(vertices_bxnx3, faces_bxfx3):
+    """utils/mesh_utils.py:16-39: mean over edge-adjacent face pairs of 1 - n_i.n_j (adjacency from sample 0)."""
+    B, F = faces_bxfx3.shape[0], faces_bxfx3.shape[1]
+    tri = vertices_bxnx3[torch.arange(B, device=faces_bxfx3.device).reshape(B, 1, 1), faces_bxfx3.long()]          # (B,F,3,3)
+    n = face_unit_normals(tri[:, :, 0], tri[:, :, 1], tri[:, :, 2])
+    with torch.no_grad():
+        pairs = tet_face_adj_m_f_idx(tri[0].float())
+    if pairs.sum() == 0:
+        return torch.zeros(B, device=faces_bxfx3.device).float()
+    return (1 - (n[:, pairs[0]] * n[:, pairs[1]]).sum(dim=-1)).mean(dim=-1)
+
+
+def sample_faces_uniform(face_bxfx3x3, each_face_num=20):
+    """utils/mesh_utils.py:290-299; the two torch.rand calls keep the reference's order (sqrt'ed u first, then v)."""
+    B, F = face_bxfx3x3.shape[0], face_bxfx3x3.shape[1]
+    u = torch.rand(size=(B, F, each_face_num, 1), device=face_bxfx3x3.device).sqrt()
+    v = torch.rand(size=(B, F, each_face_num, 1), device=face_bxfx3x3.device)
+    w0, w1, w2 = 1 - u, u * (1 - v), u * v
+    return w0 * face_bxfx3x3[:, :, 0:1] + w1 * face_bxfx3x3[:, :, 1:2] + w2 * face_bxfx3x3[:, :, 2:3]
+
+
+def one_sided_chamfer_dense(a_bxnx3, b_bxmx3, eps=1e-10):
+    """utils/mesh_utils.py:360-366: distance of every a to its nearest b (gradient flows to a only through the difference)."""
+    from .search import nearest_neighbor_index
+    idx = nearest_neighbor_index(a_bxnx3, b_bxmx3).long()
+    nearest = torch.gather(b_bxmx3, 1, idx.unsqueeze(-1).expand(-1, -1, 3))
+    return ((a_bxnx3 - nearest).pow(2).sum(dim=-1) + eps).sqrt()
+
+
+def point_to_faces_distance_dense(a_bxnx3, mesh_bxfx3x3, eps=1e-10):
+    """utils/mesh_utils.py:368-374."""
+    n_face = torch.full((mesh_bxfx3x3.shape[0],), float(mesh_bxfx3x3.shape[1]), device=mesh_bxfx3x3.device)
+    d, _ = tet_analytic_distance_f_batch(a_bxnx3, mesh_bxfx3x3, n_face)
+    return (d + eps).sqrt()

@@ -103,3 +103,29 @@ def test_thread_per_call_pattern_is_safe():
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errors, errors
+
+
+def test_mesh_utils_mirrors_match_oracle():
+    """The dense utils/mesh_utils.py mirrors (the functions DefTet.forward calls per sample in the reference)."""
+    from deftet_b200 import surface
+    g, pos, tet, verts, faces, f3, ft2, gt, pts, v, f, radii = _inputs(res=8, B=2)
+    soup = orc_e.gather_tets(pos, tet)
+    occ = np.stack([orc.check_sign(verts[b].numpy(), f, soup[b].mean(dim=1).unsqueeze(0).numpy())[0] for b in range(2)]).astype(np.float32)
+    bnd = orc_s.get_boundary_index(f3, ft2, torch.from_numpy(occ))[0]
+    p1 = pos[0:1].clone().requires_grad_(True)
+    ref_n = orc_s.normal_loss(p1, bnd)
+    surf = orc_s.gather_faces(p1, bnd)
+    ref_d = orc_s.point_mesh_distance(gt[0:1], surf)
+    q = gt[0:1, :500] * 1.03
+    ref_c = orc_s.chamfer(q, gt[0:1])
+    (ref_n.sum() + ref_d.mean()).backward()
+    dp = pos[0:1].cuda().requires_grad_(True)
+    dn = surface.surface_normal_loss_dense(dp, bnd.cuda().unsqueeze(0))
+    dsurf = dp[:, bnd.cuda().reshape(-1)].reshape(1, -1, 3, 3)
+    dd = surface.point_to_faces_distance_dense(gt[0:1].cuda(), dsurf)
+    dc = surface.one_sided_chamfer_dense(q.cuda(), gt[0:1].cuda())
+    (dn.sum() + dd.mean()).backward()
+    assert rel_err(dn, ref_n.detach()) < 1e-5 and rel_err(dd, ref_d.detach()) < 1e-5 and rel_err(dc, ref_c) < 1e-5
+    assert rel_err(dp.grad, p1.grad) < 1e-5
+    s = surface.sample_faces_uniform(dsurf.detach(), 20)
+    assert s.shape == (1, bnd.shape[0], 20, 3)
