@@ -91,10 +91,10 @@ __global__ void __launch_bounds__(256) rd_pairs_kernel(const float* __restrict__
             ++o;
         }
 }
-// pad keys beyond the real pair count so that they sort to the end
-__global__ void rd_pad_kernel(u64* keys, unsigned* vals, const unsigned* total, size_t cap) {
+// pad keys beyond the real pair count so that they sort to the end (pad_key = one past the largest valid key)
+__global__ void rd_pad_kernel(u64* keys, unsigned* vals, const unsigned* total, size_t cap, u64 pad_key) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < cap && i >= *total) { keys[i] = ~0ull; vals[i] = 0xffffffffu; }
+    if (i < cap && i >= *total) { keys[i] = pad_key; vals[i] = 0xffffffffu; }
 }
 
 // cell_end[c] = cell_start[c+1] (the pair list is sorted by cell); flags overflow of the pair capacity
@@ -260,7 +260,7 @@ static int rd_kpad(int K) { int p = 32; while (p < K) p <<= 1; return p; }
 
 extern "C" size_t dtb_sparse_render_workspace(int B, int P, int F, int R, long long pair_capacity) {
     (void)P;
-    if (R <= 0) R = 128;
+    if (R <= 0) R = 64;
     if (pair_capacity <= 0) pair_capacity = (long long)B * F * 8;
     size_t cells = (size_t)B * R * R, n = (size_t)pair_capacity;
     return align_up((size_t)B * 16, 256) + 2 * align_up((size_t)B * F * 4, 256) + 2 * align_up(cells * 4, 256) + 2 * align_up(n * 8, 256) +
@@ -268,7 +268,7 @@ extern "C" size_t dtb_sparse_render_workspace(int B, int P, int F, int R, long l
 }
 
 // pixel_coords (B,P,2), render_ranges (B,P,2), face_z (B,F,3), face_xy (B,F,3,2), face_feat (B,F,3,D) ->
-// out_feat (B,P,K,D) f32, out_idx (B,P,K) i64.  R: cells per axis of the face-binning grid (<=0: 128);
+// out_feat (B,P,K,D) f32, out_idx (B,P,K) i64.  R: cells per axis of the face-binning grid (<=0: 64);
 // pair_capacity: room for (cell, face) pairs (<=0: 8 per face); *overflow (device int) is set if it was too small.
 extern "C" int dtb_sparse_render_forward(const float* pixel_coords, const float* render_ranges, const float* face_z, const float* face_xy,
                                          const float* face_feat, int B, int P, int F, int D, int K, float eps, int R, long long pair_capacity,
@@ -278,7 +278,7 @@ extern "C" int dtb_sparse_render_forward(const float* pixel_coords, const float*
     DTB_REQUIRE(pixel_coords && render_ranges && out_feat && out_idx && overflow && D > 0, "sparse_render_forward: bad argument");
     DTB_REQUIRE(K <= 1024, "sparse_render_forward: K=%d > 1024 not supported", K);
     cudaStream_t st = (cudaStream_t)stream;
-    if (R <= 0) R = 128;
+    if (R <= 0) R = 64;
     if (pair_capacity <= 0) pair_capacity = (long long)B * F * 8;
     size_t cells = (size_t)B * R * R, cap = (size_t)pair_capacity;
     Workspace ws(workspace, workspace_bytes);
@@ -308,12 +308,11 @@ extern "C" int dtb_sparse_render_forward(const float* pixel_coords, const float*
         if (rc) return rc;
         rd_pairs_kernel<<<gf, 256, 0, st>>>(face_xy, F, R, bbox, pair_off, cap, k0, v0, cstart);
         DTB_LAUNCH_CHECK("rd_pairs");
-        rd_pad_kernel<<<cdiv((long long)cap, 256), 256, 0, st>>>(k0, v0, total, cap);
-        DTB_LAUNCH_CHECK("rd_pad");
         u64 maxkey = (u64)cells * (u64)F;
         int bits = 1; while (bits < 64 && (maxkey >> bits)) ++bits;
-        rc = radix_sort_pairs_u64(k0, v0, k1, v1, cap, 64 /* padded keys are ~0 */, sows, sob, st);
-        (void)bits;
+        rd_pad_kernel<<<cdiv((long long)cap, 256), 256, 0, st>>>(k0, v0, total, cap, maxkey);
+        DTB_LAUNCH_CHECK("rd_pad");
+        rc = radix_sort_pairs_u64(k0, v0, k1, v1, cap, bits, sows, sob, st);
         if (rc) return rc;
     }
     int rc = exclusive_scan_u32(cstart, cstart, cells, nullptr, sws2, sb2, st);

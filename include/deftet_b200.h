@@ -226,7 +226,7 @@ int dtb_host_colaps_v(const float* point_p, int32_t* map_array_p, int32_t* inver
  * pixel_coords (B,P,2), render_ranges (B,P,2) [zmin,zmax], face_z (B,F,3), face_xy (B,F,3,2), face_feat (B,F,3,D)
  * -> out_feat (B,P,K,D) f32 and out_idx (B,P,K) i64: per pixel the first K faces (ascending id) containing it with
  * interpolated z in range, ordered by z descending; void slots are 0 / -1.  eps: kaolin's 1e-8.
- * R: cells per axis of the face-binning grid (<=0: 128); pair_capacity: capacity for (cell, face) pairs (<=0: 8 per
+ * R: cells per axis of the face-binning grid (<=0: 64); pair_capacity: capacity for (cell, face) pairs (<=0: 8 per
  * face); *overflow (device int32) is set to 1 when it was too small (results are then invalid: retry larger).
  * backward ACCUMULATES into g_xy (B,F,3,2) and g_feat (B,F,3,D); no gradient to z or the pixel. */
 size_t dtb_sparse_render_workspace(int B, int P, int F, int R, long long pair_capacity);
