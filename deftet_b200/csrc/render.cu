@@ -173,41 +173,60 @@ __global__ void __launch_bounds__(RD_WARPS * 32) rd_forward_kernel(
     while (n2 < count) n2 <<= 1;
     for (int i = count + lane; i < n2; i += 32) { s_depth[i] = -3.4e38f; s_face[i] = -1; s_w1[i] = 0.f; s_w2[i] = 0.f; }
     __syncwarp();
-    // the slot order is encoded by giving equal depths a deterministic order through a stable network on (depth, face id)
+    // every lane owns one compare-exchange per step: pair index p -> (i, l = i | j) with bit log2(j) of i cleared
     for (int k = 2; k <= n2; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = lane; i < n2; i += 32) {
-                int l = i ^ j;
-                if (l > i) {
-                    bool up = (i & k) == 0;              // "up" = this half sorted in final (descending-depth) order
-                    float da = s_depth[i], db = s_depth[l];
-                    int fa = s_face[i], fb = s_face[l];
-                    // a should come before b when depth larger, or equal depth and smaller face id (void = -1 sorts last)
-                    bool a_first = (da > db) || (da == db && (unsigned)fa < (unsigned)fb);
-                    if (a_first != up) {
-                        s_depth[i] = db; s_depth[l] = da; s_face[i] = fb; s_face[l] = fa;
-                        float t = s_w1[i]; s_w1[i] = s_w1[l]; s_w1[l] = t;
-                        t = s_w2[i]; s_w2[i] = s_w2[l]; s_w2[l] = t;
-                    }
+            for (int p = lane; p < (n2 >> 1); p += 32) {
+                int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                int l = i | j;
+                bool up = (i & k) == 0;              // "up" = this half sorted in final (descending-depth) order
+                float da = s_depth[i], db = s_depth[l];
+                int fa = s_face[i], fb = s_face[l];
+                // a comes first when its depth is larger, or equal depth and smaller face id (void = -1 sorts last)
+                bool a_first = (da > db) || (da == db && (unsigned)fa < (unsigned)fb);
+                if (a_first != up) {
+                    s_depth[i] = db; s_depth[l] = da; s_face[i] = fb; s_face[l] = fa;
+                    float t = s_w1[i]; s_w1[i] = s_w1[l]; s_w1[l] = t;
+                    t = s_w2[i]; s_w2[i] = s_w2[l]; s_w2[l] = t;
                 }
             }
             __syncwarp();
         }
     // write the K slots of this pixel
     long long* oi = out_idx + po * K;
-    for (int k = lane; k < K; k += 32) oi[k] = (k < count) ? (long long)s_face[k] : -1ll;
     float* of = out_feat + po * (size_t)K * D;
     const float* ff = face_feat + (size_t)b * F * 3 * D;
-    for (int e = lane; e < K * D; e += 32) {
-        int k = e / D, c = e - k * D;
-        float v = 0.f;
-        if (k < count) {
-            int f = s_face[k];
-            float w1 = s_w1[k], w2 = s_w2[k], w0 = 1.f - w1 - w2;
-            const float* q = ff + (size_t)f * 3 * D;
-            v = w0 * q[c] + w1 * q[D + c] + w2 * q[2 * D + c];
+    const bool vec4 = (D == 4) && ((((size_t)of) | ((size_t)ff)) & 15) == 0;
+    if (vec4) {                                           // RGBA features: one 16-byte store per slot
+        float4* of4 = reinterpret_cast<float4*>(of);
+        for (int k = lane; k < K; k += 32) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            long long id = -1ll;
+            if (k < count) {
+                int f = s_face[k];
+                id = f;
+                float w1 = s_w1[k], w2 = s_w2[k], w0 = 1.f - w1 - w2;
+                const float4* q = reinterpret_cast<const float4*>(ff + (size_t)f * 12);
+                float4 a = __ldg(q), bq = __ldg(q + 1), c = __ldg(q + 2);
+                o.x = w0 * a.x + w1 * bq.x + w2 * c.x; o.y = w0 * a.y + w1 * bq.y + w2 * c.y;
+                o.z = w0 * a.z + w1 * bq.z + w2 * c.z; o.w = w0 * a.w + w1 * bq.w + w2 * c.w;
+            }
+            of4[k] = o;
+            oi[k] = id;
         }
-        of[e] = v;
+    } else {
+        for (int k = lane; k < K; k += 32) oi[k] = (k < count) ? (long long)s_face[k] : -1ll;
+        for (int e = lane; e < K * D; e += 32) {
+            int k = e / D, c = e - k * D;
+            float v = 0.f;
+            if (k < count) {
+                int f = s_face[k];
+                float w1 = s_w1[k], w2 = s_w2[k], w0 = 1.f - w1 - w2;
+                const float* q = ff + (size_t)f * 3 * D;
+                v = w0 * q[c] + w1 * q[D + c] + w2 * q[2 * D + c];
+            }
+            of[e] = v;
+        }
     }
 }
 
