@@ -129,3 +129,44 @@ def test_mesh_utils_mirrors_match_oracle():
     assert rel_err(dp.grad, p1.grad) < 1e-5
     s = surface.sample_faces_uniform(dsurf.detach(), 20)
     assert s.shape == (1, bnd.shape[0], 20, 3)
+
+
+def test_pybind_shaped_extension_objects(monkeypatch):
+    """The module-level extension objects the reference's Python wrappers call (in-place output conventions)."""
+    import importlib
+    import os
+    import sys
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "deftet_b200", "dropin")
+    monkeypatch.syspath_prepend(root)
+    for m in [k for k in sys.modules if k == "layers" or k.startswith("layers.") or k == "_fallthrough"]:
+        monkeypatch.delitem(sys.modules, m)
+    nn_mod = importlib.import_module("layers.nearest_neighbor.nearest_neighbor")
+    ad_mod = importlib.import_module("layers.DefTet.tet_analytic_distance_batch.utils")
+    fa_mod = importlib.import_module("layers.DefTet.tet_face_adj_m_idx.utils")
+    cc_mod = importlib.import_module("layers.DefTet.check_condition_tetrahedron_base.utils")
+    g, pos, tet = deformed_grid(8, 1, seed=2)
+    gen = torch.Generator().manual_seed(0)
+    q = (torch.rand(1, 300, 3, generator=gen) - 0.5)
+    p = (torch.rand(1, 500, 3, generator=gen) - 0.5)
+    res = torch.zeros(1, 300, dtype=torch.int32, device="cuda")
+    nn_mod.native.forward(q.cuda(), p.cuda(), res, 1, 300, 500, 3)
+    assert np.array_equal(res.cpu().numpy().astype(np.int64), orc.nearest_neighbor(q.numpy(), p.numpy()))
+    faces = torch.rand(1, 60, 3, 3, generator=gen) - 0.5
+    cf = torch.zeros(1, 300, 1, device="cuda")
+    cd = torch.zeros(1, 300, 1, device="cuda")
+    ad_mod.tet_analytic_distance_batch.forward(q.cuda(), faces.cuda(), cf, cd, torch.tensor([60.0]).cuda())
+    d_ref, f_ref = orc.point_face_distance(q.numpy(), faces.numpy())
+    assert np.array_equal(cf.cpu().numpy(), f_ref) and np.array_equal(cd.cpu().numpy(), d_ref)
+    dld = torch.zeros(1, 60, 3, 3, device="cuda")
+    gd = torch.rand(1, 300, 1, generator=gen)
+    ad_mod.tet_analytic_distance_batch.backward(q.cuda(), faces.cuda(), cf, gd.cuda(), dld)
+    assert rel_err(dld, orc.point_face_distance_bwd(q.numpy(), faces.numpy(), f_ref, gd.numpy())) < 1e-5
+    adj = -torch.ones(60, 30, device="cuda")
+    fa_mod.tet_face_adj_m_idx.forward(faces[0].cuda(), adj)
+    assert np.array_equal(adj.cpu().numpy(), orc.face_adjacency(faces[0].numpy())[0])
+    soup = orc_e.gather_tets(pos, tet)
+    cond = -torch.ones(1, 300, 1, device="cuda")
+    cc_mod.check_condition_cuda_tet_base.forward(soup.cuda().contiguous(), q.cuda().contiguous(), cond, None)
+    assert np.array_equal(cond.cpu().numpy(), orc.point_in_tet(soup.numpy(), q.numpy()))
+    with pytest.raises(RuntimeError):
+        cc_mod.check_condition_cuda_tet_base.backward()
