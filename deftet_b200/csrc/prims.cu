@@ -5,7 +5,7 @@
 namespace dtb {
 
 // =====================================================================================================
-// exclusive scan: blocks of SCAN_TILE = 512 threads x 4 items
+// exclusive scan: tiles of SCAN_TILE = 512 threads x 4 items; `out` may alias `in` (a tile reads its items before writing them)
 // =====================================================================================================
 constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_ITEMS = 4;
@@ -38,31 +38,10 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* s
     return x - v + s_warp[warp];
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const unsigned* __restrict__ in, size_t n, unsigned* __restrict__ block_sums) {
-    size_t base = (size_t)blockIdx.x * SCAN_TILE;
-    unsigned s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        size_t i = base + (size_t)k * SCAN_THREADS + threadIdx.x;
-        if (i < n) s += in[i];
-    }
-    __shared__ unsigned sw[SCAN_THREADS / 32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        unsigned t = threadIdx.x < SCAN_THREADS / 32 ? sw[threadIdx.x] : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
-    }
-}
-
 // scans one tile per block; adds block_offsets[blockIdx.x] when given
-__global__ void __launch_bounds__(SCAN_THREADS) scan_down_kernel(const unsigned* __restrict__ in, unsigned* __restrict__ out, size_t n,
+__global__ void __launch_bounds__(SCAN_THREADS) scan_down_kernel(const unsigned* in, unsigned* out, size_t n,
                                                                  const unsigned* __restrict__ block_offsets, unsigned* __restrict__ total,
-                                                                 unsigned* __restrict__ out2) {
+                                                                 unsigned* out2) {
     __shared__ unsigned s_warp[33];
     size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
     unsigned v[SCAN_ITEMS];
@@ -84,13 +63,62 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_down_kernel(const unsigned*
     if (total && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total = off + btot;
 }
 
-size_t scan_workspace_bytes(size_t n) {
-    size_t bytes = 0;
-    while (n > (size_t)SCAN_TILE) {
-        n = (n + SCAN_TILE - 1) / SCAN_TILE;
-        bytes += align_up(n * sizeof(unsigned), 256);
+// Single-pass chained scan with decoupled look-back: tiles take a ticket (scheduling order, so a tile only ever waits
+// for tiles that are already running), publish (flag, value) as ONE 64-bit word -- flag 1 = tile aggregate, 2 = inclusive
+// prefix -- and thread 0 sums the predecessors' words backwards until it meets an inclusive prefix.
+__global__ void __launch_bounds__(SCAN_THREADS) scan_onepass_kernel(const unsigned* in, unsigned* out,
+                                                                   unsigned* out2, size_t n, unsigned long long* state,
+                                                                   unsigned* ticket, unsigned* __restrict__ total) {
+    __shared__ unsigned s_warp[33];
+    __shared__ unsigned s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    size_t base = (size_t)tile * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    unsigned v[SCAN_ITEMS];
+    unsigned tsum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        tsum += v[k];
     }
-    return bytes + 256;
+    unsigned btot;
+    unsigned ex = block_exclusive_scan(tsum, s_warp, btot);
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* st = state;
+        unsigned prefix = 0;
+        if (tile == 0) {
+            st[0] = (2ull << 32) | btot;
+        } else {
+            st[tile] = (1ull << 32) | btot;
+            __threadfence();
+            int p = (int)tile - 1;
+            for (;;) {
+                unsigned long long w = st[p];
+                unsigned flag = (unsigned)(w >> 32);
+                if (flag == 0u) continue;                 // predecessor has not published yet
+                prefix += (unsigned)w;
+                if (flag == 2u) break;
+                --p;
+            }
+            st[tile] = (2ull << 32) | (prefix + btot);
+        }
+        __threadfence();
+        s_prefix = prefix;
+        if (total && (size_t)(tile + 1) * SCAN_TILE >= n) *total = prefix + btot;
+    }
+    __syncthreads();
+    ex += s_prefix;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) { out[base + k] = ex; if (out2) out2[base + k] = ex; }
+        ex += v[k];
+    }
+}
+
+size_t scan_workspace_bytes(size_t n) {
+    size_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    return align_up((nb + 2) * sizeof(unsigned long long), 256) + 256;
 }
 
 int exclusive_scan_u32(const unsigned* in, unsigned* out, size_t n, unsigned* total, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -109,15 +137,14 @@ int exclusive_scan_u32_dup(const unsigned* in, unsigned* out, unsigned* out2, si
         return DTB_OK;
     }
     size_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
-    size_t need = align_up(nb * sizeof(unsigned), 256);
+    size_t need = align_up((nb + 2) * sizeof(unsigned long long), 256);
     if (ws_bytes < need || !ws) { set_error("exclusive_scan: workspace too small"); return DTB_EWORKSPACE; }
-    unsigned* sums = (unsigned*)ws;
-    scan_reduce_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, sums);
-    DTB_LAUNCH_CHECK("scan_reduce");
-    int rc = exclusive_scan_u32(sums, sums, nb, nullptr, (char*)ws + need, ws_bytes - need, st);
-    if (rc) return rc;
-    scan_down_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, sums, total, out2);
-    DTB_LAUNCH_CHECK("scan_down");
+    if (nb >= (1ull << 31)) { set_error("exclusive_scan: too many tiles"); return DTB_EOVERFLOW; }
+    unsigned long long* state = (unsigned long long*)ws;
+    unsigned* ticket = (unsigned*)(state + nb);
+    DTB_CUDA(cudaMemsetAsync(ws, 0, (nb + 1) * sizeof(unsigned long long), st));
+    scan_onepass_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, out2, n, state, ticket, total);
+    DTB_LAUNCH_CHECK("scan_onepass");
     return DTB_OK;
 }
 
