@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_down_kernel(const unsigned*
 
 // Single-pass chained scan with decoupled look-back: tiles take a ticket (scheduling order, so a tile only ever waits
 // for tiles that are already running), publish (flag, value) as ONE 64-bit word -- flag 1 = tile aggregate, 2 = inclusive
-// prefix -- and thread 0 sums the predecessors' words backwards until it meets an inclusive prefix.
+// prefix -- and warp 0 sums the predecessors' words backwards, 32 at a time, until it meets an inclusive prefix.
 __global__ void __launch_bounds__(SCAN_THREADS) scan_onepass_kernel(const unsigned* in, unsigned* out,
                                                                    unsigned* out2, size_t n, unsigned long long* state,
                                                                    unsigned* ticket, unsigned* __restrict__ total) {
@@ -84,28 +84,40 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_onepass_kernel(const unsign
     }
     unsigned btot;
     unsigned ex = block_exclusive_scan(tsum, s_warp, btot);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {                       // warp 0 publishes and looks back, 32 predecessors per step
         volatile unsigned long long* st = state;
+        const int lane = threadIdx.x;
         unsigned prefix = 0;
         if (tile == 0) {
-            st[0] = (2ull << 32) | btot;
+            if (lane == 0) st[0] = (2ull << 32) | btot;
         } else {
-            st[tile] = (1ull << 32) | btot;
+            if (lane == 0) { st[tile] = (1ull << 32) | btot; }
             __threadfence();
-            int p = (int)tile - 1;
+            int hi = (int)tile - 1;               // window = tiles hi, hi-1, ..., hi-31
             for (;;) {
-                unsigned long long w = st[p];
+                int p = hi - lane;
+                unsigned long long w = (p >= 0) ? st[p] : (2ull << 32);      // before tile 0: an inclusive prefix of 0
                 unsigned flag = (unsigned)(w >> 32);
-                if (flag == 0u) continue;                 // predecessor has not published yet
-                prefix += (unsigned)w;
-                if (flag == 2u) break;
-                --p;
+                unsigned ready = __ballot_sync(0xffffffffu, flag != 0u);
+                unsigned incl = __ballot_sync(0xffffffffu, flag == 2u);
+                // lanes 0..first-1 must all be published, where first = nearest inclusive prefix in the window (or 32)
+                int first = incl ? (__ffs(incl) - 1) : 32;
+                unsigned need = (first >= 32) ? 0xffffffffu : ((2u << first) - 1u);
+                if ((ready & need) != need) continue;                       // somebody in front has not published yet: re-read
+                unsigned val = (lane <= first) ? (unsigned)w : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                prefix += val;
+                if (first < 32) break;
+                hi -= 32;
             }
-            st[tile] = (2ull << 32) | (prefix + btot);
+            if (lane == 0) st[tile] = (2ull << 32) | (prefix + btot);
         }
         __threadfence();
-        s_prefix = prefix;
-        if (total && (size_t)(tile + 1) * SCAN_TILE >= n) *total = prefix + btot;
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (total && (size_t)(tile + 1) * SCAN_TILE >= n) *total = prefix + btot;
+        }
     }
     __syncthreads();
     ex += s_prefix;
