@@ -43,8 +43,34 @@ __device__ __forceinline__ unsigned long long brick_reach_mask(float qx, float q
 }
 
 // V must provide:  float bound() const   -- current best value (squared distance) for pruning
+//                  static float no_hit()  -- the value bound() has while nothing has been accepted (initial best)
 //                  void item(const float4& it)  -- evaluate one item (x,y,z = binned position, w = index bits)
 // `inflate`: radius by which an item may extend beyond the position it was binned with (0 for points).
+// visit one brick: skip if empty / out of reach, else scan the cells the current search ball can reach
+template <typename V>
+__device__ __forceinline__ void brick_visit(float qx, float qy, float qz, const GridParams& g, int NB, int bx, int by, int bz, float bw,
+                                            float shrink, unsigned long long skip_bits, const unsigned* __restrict__ cell_start,
+                                            const unsigned* __restrict__ cell_end, const float4* __restrict__ sorted,
+                                            const unsigned long long* __restrict__ mask, size_t cell_base, V& vis) {
+    const size_t brick = ((size_t)bz * NB + by) * NB + bx;
+    unsigned long long m = __ldg(mask + (cell_base >> 6) + brick) & ~skip_bits;
+    if (!m) return;
+    const float lx = g.ox + (float)bx * bw, ly = g.oy + (float)by * bw, lz = g.oz + (float)bz * bw;
+    if (box_dist2(qx, qy, qz, lx, ly, lz, bw, shrink) > vis.bound()) return;
+    // keep only the cells inside the bounding cube of the current search ball (radius sqrt(best) + shrink, padded by
+    // 1 % of a cell against the rounding of the cell assignment)
+    m &= brick_reach_mask(qx, qy, qz, sqrtf(vis.bound()) * 1.0001f + shrink + 0.01f * g.h, lx, ly, lz, g.inv_h);
+    const size_t c0 = cell_base + brick * 64;
+    while (m) {
+        const int k = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const float cxl = lx + (float)(k & 3) * g.h, cyl = ly + (float)((k >> 2) & 3) * g.h, czl = lz + (float)(k >> 4) * g.h;
+        if (box_dist2(qx, qy, qz, cxl, cyl, czl, g.h, shrink) > vis.bound()) continue;
+        const unsigned j0 = __ldg(cell_start + c0 + k), j1 = __ldg(cell_end + c0 + k);
+        for (unsigned j = j0; j < j1; ++j) vis.item(__ldg(sorted + j));
+    }
+}
+
 template <typename V>
 __device__ __forceinline__ void brick_walk(float qx, float qy, float qz, const GridParams& g, int G, float inflate,
                                            const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
@@ -55,21 +81,19 @@ __device__ __forceinline__ void brick_walk(float qx, float qy, float qz, const G
     // rounding slack of the cell assignment floor((x-o)*inv_h): a few ulps of the coordinates, far below 1e-3 h
     const float slack = 1e-3f * g.h + 1e-6f * (fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz) + (float)G * g.h);
     const float shrink = inflate + slack;
-    const int bx0 = cell_coord(qx, g.ox, g.inv_h, G) >> 2, by0 = cell_coord(qy, g.oy, g.inv_h, G) >> 2,
-              bz0 = cell_coord(qz, g.oz, g.inv_h, G) >> 2;
-    const size_t brick_base = cell_base >> 6;
-    unsigned home_cell;
-    {   // start with the query's own cell so that the bound is finite before the first brick is filtered
-        home_cell = cell_index(cell_coord(qx, g.ox, g.inv_h, G), cell_coord(qy, g.oy, g.inv_h, G), cell_coord(qz, g.oz, g.inv_h, G), G, true);
+    const int cx = cell_coord(qx, g.ox, g.inv_h, G), cy = cell_coord(qy, g.oy, g.inv_h, G), cz = cell_coord(qz, g.oz, g.inv_h, G);
+    const int bx0 = cx >> 2, by0 = cy >> 2, bz0 = cz >> 2;
+    const unsigned home_cell = cell_index(cx, cy, cz, G, true);
+    {   // the query's own cell first, so that the bound is finite before anything is filtered
         const size_t hc = cell_base + home_cell;
         const unsigned j0 = __ldg(cell_start + hc), j1 = __ldg(cell_end + hc);
         for (unsigned j = j0; j < j1; ++j) vis.item(__ldg(sorted + j));
     }
+    // phase 1: brick shells outward until something has been found (shell R = bricks at Chebyshev distance R)
+    const float no_hit = V::no_hit();                       // the visitor's bound while nothing has been accepted yet
+    int Rv = -1;                                            // shells 0..Rv have been visited
     for (int R = 0; R < NB; ++R) {
-        if (R >= 1) {
-            float lb = fmaxf((float)(R - 1) * bw * 0.999f - shrink, 0.f);
-            if (lb * lb > vis.bound()) break;
-        }
+        if (R >= 1 && vis.bound() < no_hit) break;          // a candidate exists: switch to the bounded enumeration below
         const int z0 = max(bz0 - R, 0), z1 = min(bz0 + R, NB - 1), y0 = max(by0 - R, 0), y1 = min(by0 + R, NB - 1);
         for (int bz = z0; bz <= z1; ++bz) {
             const bool zface = (bz == bz0 - R) || (bz == bz0 + R);
@@ -79,28 +103,27 @@ __device__ __forceinline__ void brick_walk(float qx, float qy, float qz, const G
                 const int step = full ? 1 : max(2 * R, 1);
                 for (int bx = bx0 - R; bx <= bx0 + R; bx += step) {
                     if (bx < xa || bx > xb) continue;
-                    const size_t brick = ((size_t)bz * NB + by) * NB + bx;
-                    unsigned long long m = __ldg(mask + brick_base + brick);
-                    if (R == 0) m &= ~(1ull << (home_cell & 63u));          // the home cell has been scanned already
-                    if (!m) continue;
-                    const float lx = g.ox + (float)bx * bw, ly = g.oy + (float)by * bw, lz = g.oz + (float)bz * bw;
-                    if (box_dist2(qx, qy, qz, lx, ly, lz, bw, shrink) > vis.bound()) continue;
-                    // keep only the cells inside the bounding cube of the current search ball (radius sqrt(best) + shrink,
-                    // padded by 1 % of a cell against the rounding of the cell assignment)
-                    m &= brick_reach_mask(qx, qy, qz, sqrtf(vis.bound()) * 1.0001f + shrink + 0.01f * g.h, lx, ly, lz, g.inv_h);
-                    const size_t c0 = cell_base + brick * 64;
-                    while (m) {
-                        const int k = __ffsll((long long)m) - 1;
-                        m &= m - 1;
-                        const float cxl = lx + (float)(k & 3) * g.h, cyl = ly + (float)((k >> 2) & 3) * g.h, czl = lz + (float)(k >> 4) * g.h;
-                        if (box_dist2(qx, qy, qz, cxl, cyl, czl, g.h, shrink) > vis.bound()) continue;
-                        const unsigned j0 = __ldg(cell_start + c0 + k), j1 = __ldg(cell_end + c0 + k);
-                        for (unsigned j = j0; j < j1; ++j) vis.item(__ldg(sorted + j));
-                    }
+                    brick_visit(qx, qy, qz, g, NB, bx, by, bz, bw, shrink, R == 0 ? (1ull << (home_cell & 63u)) : 0ull, cell_start, cell_end,
+                                sorted, mask, cell_base, vis);
                 }
             }
         }
+        Rv = R;
     }
+    if (!(vis.bound() < no_hit)) return;                    // the grid holds nothing the visitor accepts
+    // phase 2: only the bricks that the bounding cube of the search ball touches and that phase 1 has not visited.
+    // The ball only shrinks from here on, so the range computed now is a superset of what is needed.
+    const float r = sqrtf(vis.bound()) * 1.0001f + shrink + 0.01f * g.h;
+    const float ibw = g.inv_h * 0.25f;
+    const int xlo = max((int)floorf((qx - r - g.ox) * ibw), 0), xhi = min((int)floorf((qx + r - g.ox) * ibw), NB - 1);
+    const int ylo = max((int)floorf((qy - r - g.oy) * ibw), 0), yhi = min((int)floorf((qy + r - g.oy) * ibw), NB - 1);
+    const int zlo = max((int)floorf((qz - r - g.oz) * ibw), 0), zhi = min((int)floorf((qz + r - g.oz) * ibw), NB - 1);
+    for (int bz = zlo; bz <= zhi; ++bz)
+        for (int by = ylo; by <= yhi; ++by)
+            for (int bx = xlo; bx <= xhi; ++bx) {
+                if (max(max(abs(bx - bx0), abs(by - by0)), abs(bz - bz0)) <= Rv) continue;
+                brick_visit(qx, qy, qz, g, NB, bx, by, bz, bw, shrink, 0ull, cell_start, cell_end, sorted, mask, cell_base, vis);
+            }
 }
 
 }  // namespace dtb

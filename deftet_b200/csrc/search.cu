@@ -210,6 +210,7 @@ struct NnVisitor {
     float best;      // nearest_neighbor_cuda.cu:28-29: min_distance = 1e20, min_point = 0
     int bi;
     __device__ __forceinline__ float bound() const { return best; }
+    __device__ static __forceinline__ float no_hit() { return 1e20f; }
     __device__ __forceinline__ void item(const float4& p) {
         float dx = xsub(p.x, qx), dy = xsub(p.y, qy), dz = xsub(p.z, qz);
         float d = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));

@@ -189,6 +189,7 @@ struct TriVisitor {
     float rmax;             // largest centroid-to-vertex distance of the sample (inflated)
     float best; int bi;
     __device__ __forceinline__ float bound() const { return best; }
+    __device__ static __forceinline__ float no_hit() { return 10000.0f; }
     __device__ __forceinline__ void face(int f) {
         const float* t = soup + (size_t)f * 9;
         float a[3] = {__ldg(t), __ldg(t + 1), __ldg(t + 2)}, b[3] = {__ldg(t + 3), __ldg(t + 4), __ldg(t + 5)},
