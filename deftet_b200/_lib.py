@@ -42,6 +42,8 @@ def _declare(lib):
         c_f64p, c_vp, c_sz, c_vp)
     sig("dtb_tet_energies_backward", c_int, c_f32p, c_i32p, c_f32p, c_int, c_int, c_int, c_int, c_f64p, c_f32p, c_f32p,
         c_f32p, c_f32p, c_vp)
+    sig("dtb_tet_energies_backward_v4", c_int, c_f32p, c_i32p, c_f32p, c_int, c_int, c_int, c_int, c_f64p, c_f32p, c_f32p,
+        c_f32p, c_f32p, c_vp)
     sig("dtb_tet_energies_forward_soup", c_int, c_f32p, c_f32p, c_int, c_int, c_int, c_f32p, c_f32p, c_f32p, c_f64p, c_vp,
         c_sz, c_vp)
     sig("dtb_tet_energies_backward_soup", c_int, c_f32p, c_f32p, c_int, c_int, c_int, c_f64p, c_f32p, c_f32p, c_f32p,

@@ -300,6 +300,17 @@ struct ScatterDst {     // atomics into grad_pos (B,V,3)
         }
     }
 };
+struct ScatterDst4 {    // same, into a padded (B,V,4) buffer: ONE 16-byte vector reduction per vertex (red.global.add.v4.f32, sm_90+)
+    float4* grad; int V;
+    __device__ __forceinline__ void store(int b, long long, const int4& id, const float* ga, const float* gb,
+                                          const float* gc, const float* gd) const {
+        float4* g = grad + (size_t)b * V;
+        atomicAdd(g + id.x, make_float4(ga[0], ga[1], ga[2], 0.f));
+        atomicAdd(g + id.y, make_float4(gb[0], gb[1], gb[2], 0.f));
+        atomicAdd(g + id.z, make_float4(gc[0], gc[1], gc[2], 0.f));
+        atomicAdd(g + id.w, make_float4(gd[0], gd[1], gd[2], 0.f));
+    }
+};
 struct SoupDst {        // dense gradient (B,T,4,3), overwritten
     float* grad; int T;
     __device__ __forceinline__ void store(int b, long long tet, const int4&, const float* ga, const float* gb,
@@ -489,5 +500,24 @@ extern "C" int dtb_tet_inverse_v(const float* pos0, const int32_t* tet, int V, i
     if (T == 0) return DTB_OK;
     inverse_v_kernel<<<cdiv(T, 256), 256, 0, (cudaStream_t)stream>>>(pos0, tet, T, inv_v);
     DTB_LAUNCH_CHECK("inverse_v");
+    return DTB_OK;
+}
+
+// Same as dtb_tet_energies_backward, but grad_pos4 is a zero-filled PADDED (B,V,4) f32 buffer (16-byte aligned): every vertex
+// update is one 16-byte vector reduction instead of three scalar ones (the kernel is bound by the RED issue rate).
+extern "C" int dtb_tet_energies_backward_v4(const float* pos, const int32_t* tet, const float* inv_v, int B, int V, int T, int flags,
+                                            const double* stats, const float* g_amips, const float* g_edge, const float* g_volvar,
+                                            float* grad_pos4, void* stream) {
+    DTB_REQUIRE(pos && tet && grad_pos4 && stats, "tet_energies_backward_v4: null argument");
+    DTB_REQUIRE(B > 0 && T > 0, "tet_energies_backward_v4: empty batch or grid");
+    DTB_REQUIRE((((size_t)grad_pos4) & 15) == 0, "tet_energies_backward_v4: grad_pos4 must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    int tiles = cdiv(T, E_TILE);
+    IndexedSrc s{pos, V};
+    ScatterDst4 d{reinterpret_cast<float4*>(grad_pos4), V};
+    prof_begin(PROF_ENERGIES_BWD, st);
+    energies_bwd_kernel<IndexedSrc, ScatterDst4><<<tiles, E_TILE, 0, st>>>(s, d, tet, inv_v, B, T, flags, stats, g_amips, g_edge, g_volvar);
+    DTB_LAUNCH_CHECK("energies_bwd_v4");
+    prof_end(PROF_ENERGIES_BWD, st);
     return DTB_OK;
 }

@@ -60,14 +60,15 @@ class _TetEnergies(torch.autograd.Function):
         pos, tet32, inv_v, stats = ctx.saved_tensors
         B, V, _ = pos.shape
         T = tet32.shape[0]
-        grad = torch.zeros_like(pos)
+        # padded (B,V,4) accumulator: one 16-byte vector reduction per vertex update; the xyz view is returned as the gradient
+        grad4 = torch.zeros(B, V, 4, device=pos.device, dtype=torch.float32)
         gs = [None if g is None else _f32c(g) for g in (g_amips, g_edge, g_vol)]
         with torch.cuda.device(pos.device):
-            _lib.check(_lib.lib().dtb_tet_energies_backward(_lib.ptr(pos), _lib.ptr(tet32), _lib.ptr(inv_v), B, V, T,
-                                                            ctx.flags, _lib.ptr(stats), _lib.ptr(gs[0]), _lib.ptr(gs[1]),
-                                                            _lib.ptr(gs[2]), _lib.ptr(grad), _lib.stream_ptr()),
-                       "dtb_tet_energies_backward")
-        return grad, None, None, None
+            _lib.check(_lib.lib().dtb_tet_energies_backward_v4(_lib.ptr(pos), _lib.ptr(tet32), _lib.ptr(inv_v), B, V, T,
+                                                               ctx.flags, _lib.ptr(stats), _lib.ptr(gs[0]), _lib.ptr(gs[1]),
+                                                               _lib.ptr(gs[2]), _lib.ptr(grad4), _lib.stream_ptr()),
+                       "dtb_tet_energies_backward_v4")
+        return grad4[..., :3], None, None, None
 
 
 def tet_energies(pos, tet32, inv_v, flags=ALL):

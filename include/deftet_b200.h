@@ -59,6 +59,10 @@ int dtb_tet_energies_forward(const float* pos, const int32_t* tet, const float* 
 int dtb_tet_energies_backward(const float* pos, const int32_t* tet, const float* inv_v, int B, int V, int T, int flags,
                               const double* stats, const float* g_amips, const float* g_edge, const float* g_volvar,
                               float* grad_pos, void* stream);
+/* padded-gradient variant: grad_pos4 is a zero-filled (B,V,4) f32 buffer; one vector reduction per vertex update */
+int dtb_tet_energies_backward_v4(const float* pos, const int32_t* tet, const float* inv_v, int B, int V, int T, int flags,
+                                 const double* stats, const float* g_amips, const float* g_edge, const float* g_volvar,
+                                 float* grad_pos4, void* stream);
 int dtb_tet_energies_forward_soup(const float* tet_bxfx4x3, const float* inv_v, int B, int T, int flags, float* amips,
                                   float* edge, float* volvar, double* stats, void* workspace, size_t workspace_bytes,
                                   void* stream);
