@@ -57,6 +57,18 @@ __device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b)
 __device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float xsqrt(float a) { return __fsqrt_rn(a); }
 
+// ---- vertex-gradient scatter ---------------------------------------------------------------------------------
+// grad is (.., V, stride) with stride 3 (dense xyz) or 4 (padded, 16-byte aligned): with stride 4 the three components go
+// out as ONE vector reduction (REDG.E.ADD.F32x4, sm_90+), which matters because the scatter kernels are bound by the
+// reduction issue rate, not by bandwidth.
+__device__ __forceinline__ void grad_add3(float* grad, size_t vid, int stride, float x, float y, float z) {
+    if (stride == 4) {
+        atomicAdd(reinterpret_cast<float4*>(grad) + vid, make_float4(x, y, z, 0.f));
+    } else {
+        atomicAdd(grad + vid * 3, x); atomicAdd(grad + vid * 3 + 1, y); atomicAdd(grad + vid * 3 + 2, z);
+    }
+}
+
 // ---- warp / block reductions ---------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) nl_backward_pairs_kernel(const float* __r
 // chain rule n = c * (|c|^2 + eps)^-1/2, c = (b-a) x (d-a)  -> vertex gradients
 __global__ void __launch_bounds__(256) nl_backward_vertices_kernel(const float* __restrict__ pos, int V, const int32_t* __restrict__ faces,
                                                                    const int32_t* __restrict__ counts, int Fmax, const float* __restrict__ gn,
-                                                                   float* __restrict__ grad_pos) {
+                                                                   float* __restrict__ grad_pos, int gstride) {
     int b = blockIdx.y;
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= counts[b]) return;
@@ -237,13 +237,10 @@ __global__ void __launch_bounds__(256) nl_backward_vertices_kernel(const float* 
     // c = u x v : dL/du = v x gc, dL/dv = gc x u
     float gu[3] = {v[1] * gc[2] - v[2] * gc[1], v[2] * gc[0] - v[0] * gc[2], v[0] * gc[1] - v[1] * gc[0]};
     float gv[3] = {gc[1] * u[2] - gc[2] * u[1], gc[2] * u[0] - gc[0] * u[2], gc[0] * u[1] - gc[1] * u[0]};
-    float* gp = grad_pos + (size_t)b * V * 3;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        atomicAdd(gp + (size_t)fi[1] * 3 + k, gu[k]);
-        atomicAdd(gp + (size_t)fi[2] * 3 + k, gv[k]);
-        atomicAdd(gp + (size_t)fi[0] * 3 + k, -gu[k] - gv[k]);
-    }
+    float* gp = grad_pos + (size_t)b * V * gstride;
+    grad_add3(gp, (size_t)fi[1], gstride, gu[0], gu[1], gu[2]);
+    grad_add3(gp, (size_t)fi[2], gstride, gv[0], gv[1], gv[2]);
+    grad_add3(gp, (size_t)fi[0], gstride, -gu[0] - gv[0], -gu[1] - gv[1], -gu[2] - gv[2]);
 }
 
 }  // namespace dtb
@@ -334,15 +331,16 @@ extern "C" int dtb_normal_loss_forward(const float* pos, const int32_t* faces, c
 // gn_ws: (B,Fmax,3) f32 scratch (zero-filled here); accumulates into grad_pos
 extern "C" int dtb_normal_loss_backward(const float* pos, const int32_t* faces, const int32_t* counts, const int32_t* adj, const float* normals_ws,
                                         const double* acc, const float* g_loss, int B, int V, int Fmax, float* gn_ws, float* grad_pos,
-                                        void* stream) {
+                                        int grad_stride, void* stream) {
     DTB_REQUIRE(pos && faces && counts && adj && normals_ws && acc && g_loss && gn_ws && grad_pos, "normal_loss_backward: null argument");
     if (Fmax == 0) return DTB_OK;
+    DTB_REQUIRE(grad_stride == 3 || (grad_stride == 4 && (((size_t)grad_pos) & 15) == 0), "normal_loss_backward: bad grad_stride / alignment");
     cudaStream_t st = (cudaStream_t)stream;
     DTB_CUDA(cudaMemsetAsync(gn_ws, 0, (size_t)B * Fmax * 3 * sizeof(float), st));
     dim3 g(cdiv(Fmax, 256), B);
     nl_backward_pairs_kernel<<<g, 256, 0, st>>>(normals_ws, adj, counts, Fmax, acc, g_loss, gn_ws);
     DTB_LAUNCH_CHECK("nl_backward_pairs");
-    nl_backward_vertices_kernel<<<g, 256, 0, st>>>(pos, V, faces, counts, Fmax, gn_ws, grad_pos);
+    nl_backward_vertices_kernel<<<g, 256, 0, st>>>(pos, V, faces, counts, Fmax, gn_ws, grad_pos, grad_stride);
     DTB_LAUNCH_CHECK("nl_backward_vertices");
     return DTB_OK;
 }

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) pit_finalize_kernel(Src src, const float*
 // h = E^-T (g_b-g_a, g_c-g_a, g_d-g_a):  dL/dp = h,  dL/dv_i = -w_i h  (i = a,b,c,d).
 __global__ void __launch_bounds__(256) bary_backward_kernel(const float* __restrict__ pos, const int32_t* __restrict__ tet, int V,
                                                             const float* __restrict__ points, int P, const float* __restrict__ cond,
-                                                            const float* __restrict__ g_w, float* __restrict__ grad_pos,
+                                                            const float* __restrict__ g_w, float* __restrict__ grad_pos, int gstride,
                                                             float* __restrict__ grad_points) {
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -192,11 +192,9 @@ __global__ void __launch_bounds__(256) bary_backward_kernel(const float* __restr
 #pragma unroll
         for (int k = 0; k < 3; ++k) h[k] = (gb * r1[k] + gc * r2[k] + gd * r3[k]) * inv;
         if (grad_pos) {
-            float* gp = grad_pos + (size_t)b * V * 3;
+            float* gp = grad_pos + (size_t)b * V * gstride;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) atomicAdd(gp + (size_t)ids[q] * 3 + k, -w[q] * h[k]);
+            for (int q = 0; q < 4; ++q) grad_add3(gp, (size_t)ids[q], gstride, -w[q] * h[0], -w[q] * h[1], -w[q] * h[2]);
         }
     }
     if (grad_points) { grad_points[o * 3] = h[0]; grad_points[o * 3 + 1] = h[1]; grad_points[o * 3 + 2] = h[2]; }
@@ -425,14 +423,15 @@ extern "C" int dtb_point_in_tet_soup(const float* tet_bxfx4x3, const float* poin
 }
 
 extern "C" int dtb_tet_barycentric_backward(const float* pos, const int32_t* tet, const float* points, const float* cond,
-                                            const float* g_w, int B, int V, int T, int P, float* grad_pos, float* grad_points,
-                                            void* stream) {
+                                            const float* g_w, int B, int V, int T, int P, float* grad_pos, int grad_stride,
+                                            float* grad_points, void* stream) {
     (void)T;
     DTB_REQUIRE(pos && tet && points && cond && g_w, "tet_barycentric_backward: null argument");
+    DTB_REQUIRE(grad_stride == 3 || (grad_stride == 4 && (((size_t)grad_pos) & 15) == 0), "tet_barycentric_backward: grad_stride must be 3, or 4 with a 16-byte aligned buffer");
     if (P == 0 || B == 0) return DTB_OK;
     dim3 grid(cdiv(P, 256), B);
     prof_begin(PROF_BARY_BWD, (cudaStream_t)stream);
-    bary_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pos, tet, V, points, P, cond, g_w, grad_pos, grad_points);
+    bary_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pos, tet, V, points, P, cond, g_w, grad_pos, grad_stride, grad_points);
     DTB_LAUNCH_CHECK("bary_backward");
     prof_end(PROF_BARY_BWD, (cudaStream_t)stream);
     return DTB_OK;

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) chamfer_bwd_kernel(const float* __restric
                                                           const float* __restrict__ gt, int M, int V, const int32_t* __restrict__ faces,
                                                           const int32_t* __restrict__ counts, int Fmax, int S,
                                                           const float* __restrict__ u, const float* __restrict__ v,
-                                                          const float* __restrict__ g_loss, float* __restrict__ grad_pos) {
+                                                          const float* __restrict__ g_loss, float* __restrict__ grad_pos, int gstride) {
     int b = blockIdx.y;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int n = counts[b] * S;
@@ -118,11 +118,9 @@ __global__ void __launch_bounds__(256) chamfer_bwd_kernel(const float* __restric
     const int32_t* fi = faces + ((size_t)b * Fmax + f) * 3;
     float uu = u[o], vv = v[o];
     float w[3] = {1.f - uu, uu * (1.f - vv), uu * vv};
-    float* gp = grad_pos + (size_t)b * V * 3;
+    float* gp = grad_pos + (size_t)b * V * gstride;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) atomicAdd(gp + (size_t)fi[c] * 3 + k, w[c] * gq[k]);
+    for (int c = 0; c < 3; ++c) grad_add3(gp, (size_t)fi[c], gstride, w[c] * gq[0], w[c] * gq[1], w[c] * gq[2]);
 }
 
 // gather the (B, Fmax, 3, 3) vertex soup of the boundary faces (input of A4 / A5)
@@ -197,11 +195,12 @@ extern "C" int dtb_chamfer_forward(const float* q, const int32_t* nn, const floa
 
 extern "C" int dtb_chamfer_backward(const float* q, const int32_t* nn, const float* gt, const int32_t* faces, const int32_t* counts,
                                     const float* u, const float* v, const float* g_loss, int B, int V, int Fmax, int S, int M,
-                                    float* grad_pos, void* stream) {
+                                    float* grad_pos, int grad_stride, void* stream) {
     DTB_REQUIRE(q && nn && gt && faces && counts && u && v && g_loss && grad_pos, "chamfer_backward: null argument");
     if (B == 0 || Fmax == 0 || S == 0) return DTB_OK;
     dim3 grid(cdiv((long long)Fmax * S, 256), B);
-    chamfer_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q, nn, gt, M, V, faces, counts, Fmax, S, u, v, g_loss, grad_pos);
+    DTB_REQUIRE(grad_stride == 3 || (grad_stride == 4 && (((size_t)grad_pos) & 15) == 0), "chamfer_backward: bad grad_stride / alignment");
+    chamfer_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q, nn, gt, M, V, faces, counts, Fmax, S, u, v, g_loss, grad_pos, grad_stride);
     DTB_LAUNCH_CHECK("chamfer_bwd");
     return DTB_OK;
 }

@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(256) pfd_backward_kernel(const float* __restri
 __global__ void __launch_bounds__(256) pfd_backward_indexed_kernel(const float* __restrict__ points, int S, const float* __restrict__ soup,
                                                                    const int32_t* __restrict__ faces, int Fmax, int V,
                                                                    const float* __restrict__ closest_f, const float* __restrict__ closest_d,
-                                                                   const float* __restrict__ g_loss, float* __restrict__ grad_pos) {
+                                                                   const float* __restrict__ g_loss, float* __restrict__ grad_pos, int gstride) {
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S) return;
@@ -523,12 +523,10 @@ __global__ void __launch_bounds__(256) pfd_backward_indexed_kernel(const float* 
     float g9[9];
     tri_grad(fc, p, scale, g9);
     const int32_t* fi = faces + ((size_t)b * Fmax + f) * 3;
-    float* gp = grad_pos + (size_t)b * V * 3;
+    float* gp = grad_pos + (size_t)b * V * gstride;
 #pragma unroll
     for (int v = 0; v < 3; ++v)
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (g9[v * 3 + k] != 0.f) atomicAdd(gp + (size_t)fi[v] * 3 + k, g9[v * 3 + k]);
+        if (g9[v * 3] != 0.f || g9[v * 3 + 1] != 0.f || g9[v * 3 + 2] != 0.f) grad_add3(gp, (size_t)fi[v], gstride, g9[v * 3], g9[v * 3 + 1], g9[v * 3 + 2]);
 }
 
 __global__ void sqrt_mean_kernel(const float* __restrict__ d, int S, float eps, double* __restrict__ acc) {
@@ -650,11 +648,12 @@ extern "C" int dtb_point_face_distance_backward(const float* points, const float
 
 extern "C" int dtb_point_face_distance_backward_indexed(const float* points, const float* soup, const int32_t* faces, const float* closest_f,
                                                         const float* closest_d, const float* g_loss, int B, int S, int Fmax, int V,
-                                                        float* grad_pos, void* stream) {
+                                                        float* grad_pos, int grad_stride, void* stream) {
     DTB_REQUIRE(points && soup && faces && closest_f && closest_d && g_loss && grad_pos, "point_face_distance_backward_indexed: null argument");
     if (B == 0 || S == 0 || Fmax == 0) return DTB_OK;
     dim3 grid(cdiv(S, 256), B);
-    pfd_backward_indexed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, S, soup, faces, Fmax, V, closest_f, closest_d, g_loss, grad_pos);
+    DTB_REQUIRE(grad_stride == 3 || (grad_stride == 4 && (((size_t)grad_pos) & 15) == 0), "point_face_distance_backward_indexed: bad grad_stride / alignment");
+    pfd_backward_indexed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, S, soup, faces, Fmax, V, closest_f, closest_d, g_loss, grad_pos, grad_stride);
     DTB_LAUNCH_CHECK("pfd_backward_indexed");
     return DTB_OK;
 }

@@ -21,7 +21,7 @@ def _search_sigs(lib, sig):
     sig("dtb_point_in_tet_workspace", sz, i, i, i, i)
     sig("dtb_point_in_tet", i, vp, vp, vp, i, i, i, i, i, vp, vp, vp, sz, vp)
     sig("dtb_point_in_tet_soup", i, vp, vp, i, i, i, i, vp, vp, vp, sz, vp)
-    sig("dtb_tet_barycentric_backward", i, vp, vp, vp, vp, vp, i, i, i, i, vp, vp, vp)
+    sig("dtb_tet_barycentric_backward", i, vp, vp, vp, vp, vp, i, i, i, i, vp, i, vp, vp)
     sig("dtb_tet_interpolate_forward", i, vp, vp, vp, vp, i, i, i, i, vp, vp)
     sig("dtb_tet_interpolate_backward", i, vp, vp, vp, vp, vp, i, i, i, i, vp, vp, vp)
     sig("dtb_masked_mse_forward", i, vp, vp, vp, i, i, vp, vp, vp)
@@ -88,14 +88,15 @@ class _PointInTet(torch.autograd.Function):
         B, V, _ = pos.shape
         T, P = tet32.shape[0], points.shape[1]
         g_bary = _f32c(g_bary)
-        grad_pos = torch.zeros_like(pos) if ctx.needs_input_grad[0] else None
+        # padded (B,V,4) accumulator -> one vector reduction per vertex update (see include/deftet_b200.h, grad_stride)
+        grad_pos = torch.zeros(B, V, 4, device=pos.device) if ctx.needs_input_grad[0] else None
         grad_pts = torch.empty_like(points) if ctx.needs_input_grad[2] else None
         with torch.cuda.device(pos.device):
             _lib.check(_lib.lib().dtb_tet_barycentric_backward(_lib.ptr(pos), _lib.ptr(tet32), _lib.ptr(points), _lib.ptr(cond),
-                                                               _lib.ptr(g_bary), B, V, T, P, _lib.ptr(grad_pos),
+                                                               _lib.ptr(g_bary), B, V, T, P, _lib.ptr(grad_pos), 4,
                                                                _lib.ptr(grad_pts), _lib.stream_ptr()),
                        "dtb_tet_barycentric_backward")
-        return grad_pos, None, grad_pts, None
+        return (None if grad_pos is None else grad_pos[..., :3]), None, grad_pts, None
 
 
 def point_in_tet(pos, tet, points, grid_res=0):

@@ -25,18 +25,18 @@ def _surface_sigs(lib, sig):
     sig("dtb_boundary_faces", i, vp, vp, vp, i, i, i, i, vp, vp, vp, vp, sz, vp)
     sig("dtb_surface_sample", i, vp, vp, vp, vp, vp, i, i, i, i, vp, vp)
     sig("dtb_chamfer_forward", i, vp, vp, vp, vp, i, i, i, i, vp, vp, vp)
-    sig("dtb_chamfer_backward", i, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp, vp)
+    sig("dtb_chamfer_backward", i, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp, i, vp)
     sig("dtb_face_soup", i, vp, vp, vp, i, i, i, vp, vp)
     sig("dtb_point_face_distance_grid_res", i, i)
     sig("dtb_point_face_distance_workspace", sz, i, i, i, i)
     sig("dtb_point_face_distance_forward", i, vp, vp, vp, i, i, i, i, vp, vp, vp, sz, vp)
     sig("dtb_point_face_distance_backward", i, vp, vp, vp, vp, i, i, i, vp, vp)
-    sig("dtb_point_face_distance_backward_indexed", i, vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp)
+    sig("dtb_point_face_distance_backward_indexed", i, vp, vp, vp, vp, vp, vp, i, i, i, i, vp, i, vp)
     sig("dtb_sqrt_mean", i, vp, vp, i, i, f, vp, vp, vp)
     sig("dtb_face_adjacency_workspace", sz, i, i, i)
     sig("dtb_face_adjacency", i, vp, vp, vp, i, i, i, vp, vp, vp, vp, sz, vp)
     sig("dtb_normal_loss_forward", i, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp)
-    sig("dtb_normal_loss_backward", i, vp, vp, vp, vp, vp, vp, vp, i, i, i, vp, vp, vp)
+    sig("dtb_normal_loss_backward", i, vp, vp, vp, vp, vp, vp, vp, i, i, i, vp, vp, i, vp)
 
 
 def _i32c(t):
@@ -208,13 +208,13 @@ class _SurfaceChamfer(torch.autograd.Function):
         pos, faces, counts, u, v, gt, q, nn = ctx.saved_tensors
         B, V, _ = pos.shape
         Fmax, S, M = faces.shape[1], u.shape[2], gt.shape[1]
-        grad = torch.zeros_like(pos)
+        grad = torch.zeros(B, V, 4, device=pos.device)            # padded: vector reductions (grad_stride = 4)
         g = _f32c(g_loss)
         with torch.cuda.device(pos.device):
             _lib.check(_lib.lib().dtb_chamfer_backward(_lib.ptr(q), _lib.ptr(nn), _lib.ptr(gt), _lib.ptr(faces), _lib.ptr(counts),
-                                                       _lib.ptr(u), _lib.ptr(v), _lib.ptr(g), B, V, Fmax, S, M, _lib.ptr(grad),
+                                                       _lib.ptr(u), _lib.ptr(v), _lib.ptr(g), B, V, Fmax, S, M, _lib.ptr(grad), 4,
                                                        _lib.stream_ptr()), "dtb_chamfer_backward")
-        return grad, None, None, None, None, None, None
+        return grad[..., :3], None, None, None, None, None, None
 
 
 def surface_chamfer(pos, faces, counts, u, v, gt, grid_res=0):
@@ -253,14 +253,14 @@ class _SurfaceDistance(torch.autograd.Function):
         pos, faces, gt, soup, cd, cf = ctx.saved_tensors
         B, V, _ = pos.shape
         Fmax, S = faces.shape[1], gt.shape[1]
-        grad = torch.zeros_like(pos)
+        grad = torch.zeros(B, V, 4, device=pos.device)            # padded: vector reductions (grad_stride = 4)
         g = _f32c(g_loss)
         with torch.cuda.device(pos.device):
             _lib.check(_lib.lib().dtb_point_face_distance_backward_indexed(_lib.ptr(gt), _lib.ptr(soup), _lib.ptr(faces), _lib.ptr(cf),
-                                                                           _lib.ptr(cd), _lib.ptr(g), B, S, Fmax, V, _lib.ptr(grad),
+                                                                           _lib.ptr(cd), _lib.ptr(g), B, S, Fmax, V, _lib.ptr(grad), 4,
                                                                            _lib.stream_ptr()),
                        "dtb_point_face_distance_backward_indexed")
-        return grad, None, None, None, None
+        return grad[..., :3], None, None, None, None
 
 
 def surface_distance(pos, faces, counts, gt, grid_res=0):
@@ -298,14 +298,14 @@ class _NormalLoss(torch.autograd.Function):
         pos, faces, counts, adj, normals, acc = ctx.saved_tensors
         B, V, _ = pos.shape
         Fmax = faces.shape[1]
-        grad = torch.zeros_like(pos)
+        grad = torch.zeros(B, V, 4, device=pos.device)            # padded: vector reductions (grad_stride = 4)
         gn = torch.empty(B, Fmax, 3, device=pos.device)
         g = _f32c(g_loss)
         with torch.cuda.device(pos.device):
             _lib.check(_lib.lib().dtb_normal_loss_backward(_lib.ptr(pos), _lib.ptr(faces), _lib.ptr(counts), _lib.ptr(adj), _lib.ptr(normals),
-                                                           _lib.ptr(acc), _lib.ptr(g), B, V, Fmax, _lib.ptr(gn), _lib.ptr(grad),
+                                                           _lib.ptr(acc), _lib.ptr(g), B, V, Fmax, _lib.ptr(gn), _lib.ptr(grad), 4,
                                                            _lib.stream_ptr()), "dtb_normal_loss_backward")
-        return grad, None, None
+        return grad[..., :3], None, None
 
 
 def surface_normal_loss(pos, faces, counts):

@@ -34,6 +34,8 @@ extern "C" {
 #define DTB_ENERGY_ALL 7
 
 /* ---- library ------------------------------------------------------------------------------------ */
+/* Gradient buffers named grad_pos come with a grad_stride argument where noted: 3 = dense (..,V,3); 4 = padded (..,V,4), 16-byte
+ * aligned, xyz in the first three floats -- the scatter then issues one vector reduction per vertex instead of three scalar ones. */
 const char* dtb_last_error(void);
 int dtb_version(void);                 /* 100 * major + minor */
 int dtb_device_is_sm100(int device);   /* 1 if the device is compute capability 10.x, 0 if not, <0 on error */
@@ -91,8 +93,8 @@ int dtb_point_in_tet(const float* pos, const int32_t* tet, const float* points, 
 int dtb_point_in_tet_soup(const float* tet_bxfx4x3, const float* points, int B, int T, int P, int G, float* cond,
                           float* bary, void* workspace, size_t workspace_bytes, void* stream);
 int dtb_tet_barycentric_backward(const float* pos, const int32_t* tet, const float* points, const float* cond,
-                                 const float* g_w, int B, int V, int T, int P, float* grad_pos, float* grad_points,
-                                 void* stream);
+                                 const float* g_w, int B, int V, int T, int P, float* grad_pos, int grad_stride,
+                                 float* grad_points, void* stream);
 
 /* Interpolation of a per-vertex field (B,V,C) at the query points through the weights of dtb_point_in_tet
  * (the differentiable form of DefTet.paste_occ, layers/DefTet/deftet.py:132-136): out (B,P,C), zeros where
@@ -143,7 +145,7 @@ int dtb_chamfer_forward(const float* q, const int32_t* nn, const float* gt, cons
                         int M, double* acc, float* loss, void* stream);
 int dtb_chamfer_backward(const float* q, const int32_t* nn, const float* gt, const int32_t* faces, const int32_t* counts,
                          const float* u, const float* v, const float* g_loss, int B, int V, int Fmax, int S, int M,
-                         float* grad_pos, void* stream);
+                         float* grad_pos, int grad_stride, void* stream);
 int dtb_face_soup(const float* pos, const int32_t* faces, const int32_t* counts, int B, int V, int Fmax, float* soup,
                   void* stream);
 
@@ -165,7 +167,7 @@ int dtb_point_face_distance_backward(const float* points, const float* faces, co
                                      int B, int S, int Fmax, float* dldface, void* stream);
 int dtb_point_face_distance_backward_indexed(const float* points, const float* soup, const int32_t* faces,
                                              const float* closest_f, const float* closest_d, const float* g_loss, int B,
-                                             int S, int Fmax, int V, float* grad_pos, void* stream);
+                                             int S, int Fmax, int V, float* grad_pos, int grad_stride, void* stream);
 int dtb_sqrt_mean(const float* d, const int32_t* counts, int B, int S, float eps, double* acc, float* out, void* stream);
 
 /* ---- A5: boundary-face edge adjacency + normal-consistency loss -----------------------------------------------
@@ -182,7 +184,7 @@ int dtb_normal_loss_forward(const float* pos, const int32_t* faces, const int32_
                             int Fmax, float* normals_ws, double* acc, float* loss, void* stream);
 int dtb_normal_loss_backward(const float* pos, const int32_t* faces, const int32_t* counts, const int32_t* adj,
                              const float* normals_ws, const double* acc, const float* g_loss, int B, int V, int Fmax,
-                             float* gn_ws, float* grad_pos, void* stream);
+                             float* gn_ws, float* grad_pos, int grad_stride, void* stream);
 
 /* ---- A10-A14: topology builders ------------------------------------------------------------------------------
  * Device-pointer forms (tet (T,4) i32 on the device; outputs sized by the caller for the worst case; counts
