@@ -252,12 +252,25 @@ __global__ void __launch_bounds__(256) rd_backward_kernel(const float* __restric
     const float* go = g_out + o * D;
     const float* ff = face_feat + ((size_t)b * F + f) * 3 * D;
     float gw0 = 0.f, gw1 = 0.f, gw2 = 0.f;
-    for (int c = 0; c < D; ++c) {
-        float gc = go[c];
-        gw0 += gc * ff[c]; gw1 += gc * ff[D + c]; gw2 += gc * ff[2 * D + c];
-        if (g_feat) {
-            float* gf = g_feat + ((size_t)b * F + f) * 3 * D;
-            atomicAdd(gf + c, w0 * gc); atomicAdd(gf + D + c, w1 * gc); atomicAdd(gf + 2 * D + c, w2 * gc);
+    float* gfb = g_feat ? g_feat + ((size_t)b * F + f) * 3 * D : nullptr;
+    if (D == 4 && ((((size_t)go) | ((size_t)ff) | ((size_t)gfb)) & 15) == 0) {       // RGBA: 16-byte vector loads / reductions
+        float4 g4 = *reinterpret_cast<const float4*>(go);
+        const float4* f4 = reinterpret_cast<const float4*>(ff);
+        float4 a = f4[0], bq = f4[1], c = f4[2];
+        gw0 = g4.x * a.x + g4.y * a.y + g4.z * a.z + g4.w * a.w;
+        gw1 = g4.x * bq.x + g4.y * bq.y + g4.z * bq.z + g4.w * bq.w;
+        gw2 = g4.x * c.x + g4.y * c.y + g4.z * c.z + g4.w * c.w;
+        if (gfb) {
+            float4* gf4 = reinterpret_cast<float4*>(gfb);
+            atomicAdd(gf4 + 0, make_float4(w0 * g4.x, w0 * g4.y, w0 * g4.z, w0 * g4.w));
+            atomicAdd(gf4 + 1, make_float4(w1 * g4.x, w1 * g4.y, w1 * g4.z, w1 * g4.w));
+            atomicAdd(gf4 + 2, make_float4(w2 * g4.x, w2 * g4.y, w2 * g4.z, w2 * g4.w));
+        }
+    } else {
+        for (int c = 0; c < D; ++c) {
+            float gc = go[c];
+            gw0 += gc * ff[c]; gw1 += gc * ff[D + c]; gw2 += gc * ff[2 * D + c];
+            if (gfb) { atomicAdd(gfb + c, w0 * gc); atomicAdd(gfb + D + c, w1 * gc); atomicAdd(gfb + 2 * D + c, w2 * gc); }
         }
     }
     if (g_xy) {
@@ -266,8 +279,15 @@ __global__ void __launch_bounds__(256) rd_backward_kernel(const float* __restric
         float g_s = gk1 * q - gk2 * pp, g_t = -gk1 * n + gk2 * m;
         float g_m = gk2 * t + gk3 * q, g_pp = -gk2 * s - gk3 * n, g_n = -gk1 * t - gk3 * pp, g_q = gk1 * s + gk3 * m;
         float* gx = g_xy + ((size_t)b * F + f) * 6;
-        atomicAdd(gx + 0, -(g_m + g_n + g_s)); atomicAdd(gx + 1, -(g_pp + g_q + g_t));
-        atomicAdd(gx + 2, g_m); atomicAdd(gx + 3, g_pp); atomicAdd(gx + 4, g_n); atomicAdd(gx + 5, g_q);
+        if ((((size_t)gx) & 7) == 0) {                        // one 8-byte vector reduction per vertex
+            float2* gx2 = reinterpret_cast<float2*>(gx);
+            atomicAdd(gx2 + 0, make_float2(-(g_m + g_n + g_s), -(g_pp + g_q + g_t)));
+            atomicAdd(gx2 + 1, make_float2(g_m, g_pp));
+            atomicAdd(gx2 + 2, make_float2(g_n, g_q));
+        } else {
+            atomicAdd(gx + 0, -(g_m + g_n + g_s)); atomicAdd(gx + 1, -(g_pp + g_q + g_t));
+            atomicAdd(gx + 2, g_m); atomicAdd(gx + 3, g_pp); atomicAdd(gx + 4, g_n); atomicAdd(gx + 5, g_q);
+        }
     }
 }
 
