@@ -100,6 +100,9 @@ struct FacePre {
     float pad[2];                    // 32 floats = 8 x float4
 };
 constexpr int FACEPRE_FLOATS = sizeof(FacePre) / 4;
+// shared-memory stride of a staged FacePre: odd, so that lanes reading the same field of different candidates hit
+// different banks (with a stride of 32 floats every such access would be a 32-way bank conflict)
+constexpr int FACEPRE_STRIDE = FACEPRE_FLOATS + 1;
 
 __device__ __forceinline__ void face_precompute(const float* t, FacePre& f) {
 #pragma unroll
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
     const unsigned* __restrict__ qend, const float4* __restrict__ qsorted, float* __restrict__ closest_d, float* __restrict__ closest_f) {
     constexpr int WARPS = PFD_THREADS / 32;
     __shared__ float4 s_cen[PFD_CHUNK];
-    __shared__ __align__(16) float s_pre[PFD_CHUNK * FACEPRE_FLOATS];
+    __shared__ float s_pre[PFD_CHUNK * FACEPRE_STRIDE];
     __shared__ unsigned s_rs[27], s_re[27];
     __shared__ unsigned s_total;
     __shared__ unsigned s_n;
@@ -347,9 +350,12 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
                     unsigned k = base + __popc(bal & ((1u << lane) - 1u));
                     s_cen[k] = it;
                     const float4* src = preb + (size_t)__float_as_int(it.w) * 8;
-                    float4* dst = reinterpret_cast<float4*>(s_pre + (size_t)k * FACEPRE_FLOATS);
+                    float* dst = s_pre + (size_t)k * FACEPRE_STRIDE;
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) dst[m] = __ldg(src + m);
+                    for (int m = 0; m < 8; ++m) {
+                        float4 w4 = __ldg(src + m);
+                        dst[4 * m] = w4.x; dst[4 * m + 1] = w4.y; dst[4 * m + 2] = w4.z; dst[4 * m + 3] = w4.w;
+                    }
                     const FacePre& fp = *reinterpret_cast<const FacePre*>(dst);
                     // same reliability rule as face_stats_kernel (unit normal here): unreliable or invisible faces may
                     // have a reference distance larger than the distance to their centroid
@@ -372,7 +378,7 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
             }
             // the nearest-centroid face is evaluated by every lane at the same time (convergent): tight running minimum
             if (kn >= 0) {
-                const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)kn * FACEPRE_FLOATS);
+                const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)kn * FACEPRE_STRIDE);
                 float d = tri_distance_pre(fp, v.p);
                 int f = __float_as_int(s_cen[kn].w);
                 if (v.best > d || (d == v.best && v.bi >= 0 && f < v.bi)) { v.best = d; v.bi = f; }
@@ -389,7 +395,7 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
                     if (lb * lb > bound) continue;
                     if (ns < PFD_LIST) { s_list[threadIdx.x][ns++] = (unsigned char)k; }
                     else {                                   // list full (rare): evaluate on the spot
-                        const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_FLOATS);
+                        const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_STRIDE);
                         float d = tri_distance_pre(fp, v.p);
                         int f = __float_as_int(it.w);
                         if (v.best > d || (d == v.best && v.bi >= 0 && f < v.bi)) { v.best = d; v.bi = f; }
@@ -412,7 +418,7 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
                     unsigned pr = s_pairs[warp][pi];
                     int ql = (int)(pr >> 8), k = (int)(pr & 255u);
                     float qp[3] = {s_q[warp][ql][0], s_q[warp][ql][1], s_q[warp][ql][2]};
-                    const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_FLOATS);
+                    const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_STRIDE);
                     float d = tri_distance_pre(fp, qp);
                     // a face at MAX_DIS (invisible, k3 == 0) can never win the strict '<' against the initial 10000
                     if (d < FWD_MAX_DIS) atomicMin(&s_best[warp][ql], pack_df(d, __float_as_int(s_cen[k].w)));
