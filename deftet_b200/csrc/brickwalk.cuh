@@ -8,6 +8,16 @@
 
 namespace dtb {
 
+// squared distance from q to the axis-aligned box [lo, lo + w]^3-ish (per-axis lo, common width w)
+__device__ __forceinline__ float box_dist2(float qx, float qy, float qz, float lx, float ly, float lz, float w, float shrink) {
+    float dx = fmaxf(fmaxf(lx - qx, qx - (lx + w)), 0.f);
+    float dy = fmaxf(fmaxf(ly - qy, qy - (ly + w)), 0.f);
+    float dz = fmaxf(fmaxf(lz - qz, qz - (lz + w)), 0.f);
+    float d = sqrtf(dx * dx + dy * dy + dz * dz);
+    d = fmaxf(d - shrink, 0.f) * 0.9999f;
+    return d * d;
+}
+
 // occupancy-word masks of the cells of a 4x4x4 brick whose x / y / z index lies in [lo, hi] (0 <= lo <= hi <= 3)
 __device__ __forceinline__ unsigned long long brick_xmask(int lo, int hi) {
     return (unsigned long long)(((1u << (hi - lo + 1)) - 1u) << lo) * 0x1111111111111111ull;
@@ -32,14 +42,6 @@ __device__ __forceinline__ unsigned long long brick_reach_mask(float qx, float q
     return brick_xmask(x0, x1) & brick_ymask(y0, y1) & brick_zmask(z0, z1);
 }
 
-// plain squared distance from q to the box [l, l + w]^3
-__device__ __forceinline__ float raw_box_dist2(float qx, float qy, float qz, float lx, float ly, float lz, float w) {
-    float dx = fmaxf(fmaxf(lx - qx, qx - (lx + w)), 0.f);
-    float dy = fmaxf(fmaxf(ly - qy, qy - (ly + w)), 0.f);
-    float dz = fmaxf(fmaxf(lz - qz, qz - (lz + w)), 0.f);
-    return dx * dx + dy * dy + dz * dz;
-}
-
 // V must provide:  float bound() const   -- current best value (squared distance) for pruning
 //                  static float no_hit()  -- the value bound() has while nothing has been accepted (initial best)
 //                  void item(const float4& it)  -- evaluate one item (x,y,z = binned position, w = index bits)
@@ -54,20 +56,16 @@ __device__ __forceinline__ void brick_visit(float qx, float qy, float qz, const 
     unsigned long long m = __ldg(mask + (cell_base >> 6) + brick) & ~skip_bits;
     if (!m) return;
     const float lx = g.ox + (float)bx * bw, ly = g.oy + (float)by * bw, lz = g.oz + (float)bz * bw;
-    // reach of the search ball, taken once per brick (the bound only shrinks while the brick is scanned, so a stale
-    // value is conservative): a box farther than rr cannot hold anything better than the current bound
-    const float rr = sqrtf(vis.bound()) * 1.0002f + shrink;
-    const float rr2 = rr * rr;
-    if (raw_box_dist2(qx, qy, qz, lx, ly, lz, bw) > rr2) return;
-    // keep only the cells inside the bounding cube of that ball (padded by 1 % of a cell against the rounding of the
-    // cell assignment)
-    m &= brick_reach_mask(qx, qy, qz, rr + 0.01f * g.h, lx, ly, lz, g.inv_h);
+    if (box_dist2(qx, qy, qz, lx, ly, lz, bw, shrink) > vis.bound()) return;
+    // keep only the cells inside the bounding cube of the current search ball (radius sqrt(best) + shrink, padded by
+    // 1 % of a cell against the rounding of the cell assignment)
+    m &= brick_reach_mask(qx, qy, qz, sqrtf(vis.bound()) * 1.0001f + shrink + 0.01f * g.h, lx, ly, lz, g.inv_h);
     const size_t c0 = cell_base + brick * 64;
     while (m) {
         const int k = __ffsll((long long)m) - 1;
         m &= m - 1;
         const float cxl = lx + (float)(k & 3) * g.h, cyl = ly + (float)((k >> 2) & 3) * g.h, czl = lz + (float)(k >> 4) * g.h;
-        if (raw_box_dist2(qx, qy, qz, cxl, cyl, czl, g.h) > rr2) continue;
+        if (box_dist2(qx, qy, qz, cxl, cyl, czl, g.h, shrink) > vis.bound()) continue;
         const unsigned j0 = __ldg(cell_start + c0 + k), j1 = __ldg(cell_end + c0 + k);
         for (unsigned j = j0; j < j1; ++j) vis.item(__ldg(sorted + j));
     }
