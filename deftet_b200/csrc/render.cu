@@ -128,29 +128,13 @@ __device__ __forceinline__ Bary2 face_test(const float* xy, const float* z, floa
 
 constexpr int RD_WARPS = 4;
 
-// one warp per pixel.  dynamic smem: RD_WARPS * Kpad * (depth f32, face i32, w1 f32, w2 f32)
-__global__ void __launch_bounds__(RD_WARPS * 32) rd_forward_kernel(
-    const float* __restrict__ pix, const float* __restrict__ ranges, const float* __restrict__ face_z, const float* __restrict__ face_xy,
-    const float* __restrict__ face_feat, int P, int F, int D, int K, int Kpad, float eps, int R, const unsigned* __restrict__ bbox_ord,
-    const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end, const unsigned* __restrict__ cell_faces,
-    float* __restrict__ out_feat, long long* __restrict__ out_idx) {
-    extern __shared__ float smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y;
-    const long long p = (long long)blockIdx.x * RD_WARPS + warp;
-    if (p >= P) return;
-    float* s_depth = smem + (size_t)warp * Kpad * 4;
-    int* s_face = (int*)(s_depth + Kpad);
-    float* s_w1 = s_depth + 2 * Kpad;
-    float* s_w2 = s_depth + 3 * Kpad;
-    const size_t po = (size_t)b * P + p;
-    const float px = pix[po * 2], py = pix[po * 2 + 1];
-    const float zmin = ranges[po * 2], zmax = ranges[po * 2 + 1];
-    PixGrid g = pix_grid(bbox_ord, b, R);
-    const size_t cell = ((size_t)b * R + pix_cell(py, g.oy, g.inv, R)) * R + pix_cell(px, g.ox, g.inv, R);
-    const unsigned j0 = cell_start[cell], j1 = cell_end[cell];
-    const float* fxy = face_xy + (size_t)b * F * 6;
-    const float* fz = face_z + (size_t)b * F * 3;
+// Warp-cooperative hit collection for one pixel: scan the pixel's cell list in ascending face id, append hits with
+// ballot/popc (order preserved, at most K), then bitonic-sort them by (depth descending, face id ascending) in the warp's
+// shared-memory arrays.  Returns the number of hits.
+__device__ __forceinline__ int rd_collect_sorted(float px, float py, float zmin, float zmax, const float* __restrict__ fxy,
+                                                 const float* __restrict__ fz, const unsigned* __restrict__ cell_faces, unsigned j0,
+                                                 unsigned j1, int K, float eps, float* s_depth, int* s_face, float* s_w1, float* s_w2) {
+    const int lane = threadIdx.x & 31;
     int count = 0;
     for (unsigned jb = j0; jb < j1 && count < K; jb += 32) {
         unsigned j = jb + lane;
@@ -168,7 +152,6 @@ __global__ void __launch_bounds__(RD_WARPS * 32) rd_forward_kernel(
         count = min(count + __popc(hits), K);
     }
     __syncwarp();
-    // pad to a power of two and bitonic-sort by (depth descending, original slot ascending)
     int n2 = 1;
     while (n2 < count) n2 <<= 1;
     for (int i = count + lane; i < n2; i += 32) { s_depth[i] = -3.4e38f; s_face[i] = -1; s_w1[i] = 0.f; s_w2[i] = 0.f; }
@@ -192,6 +175,30 @@ __global__ void __launch_bounds__(RD_WARPS * 32) rd_forward_kernel(
             }
             __syncwarp();
         }
+    return count;
+}
+
+// one warp per pixel.  dynamic smem: RD_WARPS * Kpad * (depth f32, face i32, w1 f32, w2 f32)
+__global__ void __launch_bounds__(RD_WARPS * 32) rd_forward_kernel(
+    const float* __restrict__ pix, const float* __restrict__ ranges, const float* __restrict__ face_z, const float* __restrict__ face_xy,
+    const float* __restrict__ face_feat, int P, int F, int D, int K, int Kpad, float eps, int R, const unsigned* __restrict__ bbox_ord,
+    const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end, const unsigned* __restrict__ cell_faces,
+    float* __restrict__ out_feat, long long* __restrict__ out_idx) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const long long p = (long long)blockIdx.x * RD_WARPS + warp;
+    if (p >= P) return;
+    float* s_depth = smem + (size_t)warp * Kpad * 4;
+    int* s_face = (int*)(s_depth + Kpad);
+    float* s_w1 = s_depth + 2 * Kpad;
+    float* s_w2 = s_depth + 3 * Kpad;
+    const size_t po = (size_t)b * P + p;
+    const float px = pix[po * 2], py = pix[po * 2 + 1];
+    PixGrid g = pix_grid(bbox_ord, b, R);
+    const size_t cell = ((size_t)b * R + pix_cell(py, g.oy, g.inv, R)) * R + pix_cell(px, g.ox, g.inv, R);
+    const int count = rd_collect_sorted(px, py, ranges[po * 2], ranges[po * 2 + 1], face_xy + (size_t)b * F * 6, face_z + (size_t)b * F * 3,
+                                        cell_faces, cell_start[cell], cell_end[cell], K, eps, s_depth, s_face, s_w1, s_w2);
     // write the K slots of this pixel
     long long* oi = out_idx + po * K;
     float* of = out_feat + po * (size_t)K * D;
@@ -226,6 +233,179 @@ __global__ void __launch_bounds__(RD_WARPS * 32) rd_forward_kernel(
                 v = w0 * q[c] + w1 * q[D + c] + w2 * q[2 * D + c];
             }
             of[e] = v;
+        }
+    }
+}
+
+// ---- fused render + composite ("peel2mask", 5_rendereq/deftetrneder.py:31-64) ------------------------------------------
+// out_color (B,P,D-1) = sum_k vis_k c_k + (1 - sum_k vis_k) (white background), out_mask (B,P,1) = sum_k vis_k with
+// alpha_k = clamp(f_k[0], 1e-10, 1-1e-10), vis_k = alpha_k prod_{i<k} (1 - alpha_i) over the K depth-sorted slots (void slots
+// have f = 0, i.e. alpha = 1e-10: their tiny contribution is kept).  The (B,P,K,D) tensor is never materialised.
+constexpr int RC_MAXD = 8;
+constexpr float RC_EPS = 1e-10f;
+
+__device__ __forceinline__ void rc_slot_features(const float* __restrict__ ff, int f, float w1, float w2, int D, float* out) {
+    const float* q = ff + (size_t)f * 3 * D;
+    const float w0 = 1.f - w1 - w2;
+    for (int c = 0; c < D; ++c) out[c] = w0 * q[c] + w1 * q[D + c] + w2 * q[2 * D + c];
+}
+
+__global__ void __launch_bounds__(RD_WARPS * 32) rc_forward_kernel(
+    const float* __restrict__ pix, const float* __restrict__ ranges, const float* __restrict__ face_z, const float* __restrict__ face_xy,
+    const float* __restrict__ face_feat, int P, int F, int D, int K, int Kpad, float eps, int R, const unsigned* __restrict__ bbox_ord,
+    const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end, const unsigned* __restrict__ cell_faces,
+    float* __restrict__ out_color, float* __restrict__ out_mask) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const long long p = (long long)blockIdx.x * RD_WARPS + warp;
+    if (p >= P) return;
+    float* s_depth = smem + (size_t)warp * Kpad * 4;
+    int* s_face = (int*)(s_depth + Kpad);
+    float* s_w1 = s_depth + 2 * Kpad;
+    float* s_w2 = s_depth + 3 * Kpad;
+    const size_t po = (size_t)b * P + p;
+    const float px = pix[po * 2], py = pix[po * 2 + 1];
+    PixGrid g = pix_grid(bbox_ord, b, R);
+    const size_t cell = ((size_t)b * R + pix_cell(py, g.oy, g.inv, R)) * R + pix_cell(px, g.ox, g.inv, R);
+    const int count = rd_collect_sorted(px, py, ranges[po * 2], ranges[po * 2 + 1], face_xy + (size_t)b * F * 6, face_z + (size_t)b * F * 3,
+                                        cell_faces, cell_start[cell], cell_end[cell], K, eps, s_depth, s_face, s_w1, s_w2);
+    const float* ff = face_feat + (size_t)b * F * 3 * D;
+    float T = 1.f, mask = 0.f;
+    float col[RC_MAXD];
+    for (int c = 0; c < RC_MAXD; ++c) col[c] = 0.f;
+    for (int base = 0; base < count; base += 32) {
+        const int k = base + lane;
+        const bool valid = k < count;
+        float f[RC_MAXD];
+        float alpha = 0.f;
+        if (valid) { rc_slot_features(ff, s_face[k], s_w1[k], s_w2[k], D, f); alpha = fminf(fmaxf(f[0], RC_EPS), 1.0f - RC_EPS); }
+        float prod = valid ? 1.f - alpha : 1.f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { float y = __shfl_up_sync(0xffffffffu, prod, o); if (lane >= o) prod *= y; }
+        float excl = __shfl_up_sync(0xffffffffu, prod, 1);
+        if (lane == 0) excl = 1.f;
+        const float vis = valid ? alpha * T * excl : 0.f;
+        mask += vis;
+        for (int c = 1; c < D; ++c) col[c] += valid ? vis * f[c] : 0.f;
+        T *= __shfl_sync(0xffffffffu, prod, 31);
+    }
+    mask = warp_sum(mask);
+    for (int c = 1; c < D; ++c) col[c] = warp_sum(col[c]);
+    mask += (float)(K - count) * RC_EPS * T;                 // void slots: alpha = clamp(0) = 1e-10, (1 - 1e-10) == 1 in fp32
+    if (lane == 0) {
+        out_mask[po] = mask;
+        for (int c = 1; c < D; ++c) out_color[po * (D - 1) + (c - 1)] = col[c] + (1.f - mask);
+    }
+}
+
+// backward of the fused op: recollect the pixel's sorted hits, redo the front-to-back scan, run it backwards, scatter.
+// dynamic smem: RD_WARPS * Kpad * 6 floats (depth->alpha, face, w1, w2, T, vis*G)
+__global__ void __launch_bounds__(RD_WARPS * 32) rc_backward_kernel(
+    const float* __restrict__ pix, const float* __restrict__ ranges, const float* __restrict__ face_z, const float* __restrict__ face_xy,
+    const float* __restrict__ face_feat, int P, int F, int D, int K, int Kpad, float eps, int R, const unsigned* __restrict__ bbox_ord,
+    const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end, const unsigned* __restrict__ cell_faces,
+    const float* __restrict__ g_color, const float* __restrict__ g_mask, float* __restrict__ g_xy, float* __restrict__ g_feat) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const long long p = (long long)blockIdx.x * RD_WARPS + warp;
+    if (p >= P) return;
+    float* s_depth = smem + (size_t)warp * Kpad * 6;
+    int* s_face = (int*)(s_depth + Kpad);
+    float* s_w1 = s_depth + 2 * Kpad;
+    float* s_w2 = s_depth + 3 * Kpad;
+    float* s_T = s_depth + 4 * Kpad;
+    float* s_vg = s_depth + 5 * Kpad;
+    const size_t po = (size_t)b * P + p;
+    const float px = pix[po * 2], py = pix[po * 2 + 1];
+    PixGrid g = pix_grid(bbox_ord, b, R);
+    const size_t cell = ((size_t)b * R + pix_cell(py, g.oy, g.inv, R)) * R + pix_cell(px, g.ox, g.inv, R);
+    const float* fxy = face_xy + (size_t)b * F * 6;
+    const int count = rd_collect_sorted(px, py, ranges[po * 2], ranges[po * 2 + 1], fxy, face_z + (size_t)b * F * 3, cell_faces,
+                                        cell_start[cell], cell_end[cell], K, eps, s_depth, s_face, s_w1, s_w2);
+    if (count == 0) return;                                   // only void slots: no face receives a gradient
+    const float* ff = face_feat + (size_t)b * F * 3 * D;
+    float gc[RC_MAXD];
+    float gsum = 0.f;
+    for (int c = 1; c < D; ++c) { gc[c] = g_color[po * (D - 1) + (c - 1)]; gsum += gc[c]; }
+    const float gM = g_mask[po] - gsum;                       // out_color = C + (1 - M): dL/dM = g_mask - sum_c g_color_c
+    float* s_alpha = s_depth;                                 // depth is no longer needed after the sort
+    // pass 1 (front to back): alpha_k, T_k and vis_k * G_k with G_k = dL/dvis_k = sum_c g_color_c c_k,c + gM
+    float T = 1.f;
+    for (int base = 0; base < count; base += 32) {
+        const int k = base + lane;
+        const bool valid = k < count;
+        float f[RC_MAXD];
+        float alpha = 0.f, G = gM;
+        if (valid) {
+            rc_slot_features(ff, s_face[k], s_w1[k], s_w2[k], D, f);
+            alpha = fminf(fmaxf(f[0], RC_EPS), 1.0f - RC_EPS);
+            for (int c = 1; c < D; ++c) G += gc[c] * f[c];
+        }
+        float prod = valid ? 1.f - alpha : 1.f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { float y = __shfl_up_sync(0xffffffffu, prod, o); if (lane >= o) prod *= y; }
+        float excl = __shfl_up_sync(0xffffffffu, prod, 1);
+        if (lane == 0) excl = 1.f;
+        if (valid) { s_alpha[k] = alpha; s_T[k] = T * excl; s_vg[k] = alpha * T * excl * G; }
+        T *= __shfl_sync(0xffffffffu, prod, 31);
+    }
+    __syncwarp();
+    // pass 2 (back to front): S_k = sum_{j>k} vis_j G_j (+ the void slots), d alpha_k = T_k G_k - S_k / (1 - alpha_k)
+    float carry = (float)(K - count) * RC_EPS * T * gM;
+    const int last_base = ((count - 1) / 32) * 32;
+    for (int base = last_base; base >= 0; base -= 32) {
+        const int k = base + lane;
+        const bool valid = k < count;
+        float v = valid ? s_vg[k] : 0.f;
+        float suf = v;                                        // inclusive suffix sum across lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { float y = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += y; }
+        const float S = carry + suf - v;                      // strictly after k
+        carry += __shfl_sync(0xffffffffu, suf, 0);
+        if (!valid) continue;
+        const int f = s_face[k];
+        const float w1 = s_w1[k], w2 = s_w2[k], w0 = 1.f - w1 - w2;
+        float fv[RC_MAXD];
+        rc_slot_features(ff, f, w1, w2, D, fv);
+        const float alpha = s_alpha[k], Tk = s_T[k];
+        float G = gM;
+        for (int c = 1; c < D; ++c) G += gc[c] * fv[c];
+        float df[RC_MAXD];
+        const bool pass = (fv[0] >= RC_EPS) && (fv[0] <= 1.0f - RC_EPS);       // torch.clamp passes the gradient inside [min, max]
+        df[0] = pass ? (Tk * G - S / (1.f - alpha)) : 0.f;
+        const float vis = alpha * Tk;
+        for (int c = 1; c < D; ++c) df[c] = gc[c] * vis;
+        // scatter to the face's features and, through the weights, to its image-space vertices
+        const float* q = ff + (size_t)f * 3 * D;
+        float gw0 = 0.f, gw1 = 0.f, gw2 = 0.f;
+        for (int c = 0; c < D; ++c) { gw0 += df[c] * q[c]; gw1 += df[c] * q[D + c]; gw2 += df[c] * q[2 * D + c]; }
+        if (g_feat) {
+            float* gf = g_feat + ((size_t)b * F + f) * 3 * D;
+            if (D == 4 && (((size_t)gf) & 15) == 0) {
+                float4* gf4 = reinterpret_cast<float4*>(gf);
+                atomicAdd(gf4 + 0, make_float4(w0 * df[0], w0 * df[1], w0 * df[2], w0 * df[3]));
+                atomicAdd(gf4 + 1, make_float4(w1 * df[0], w1 * df[1], w1 * df[2], w1 * df[3]));
+                atomicAdd(gf4 + 2, make_float4(w2 * df[0], w2 * df[1], w2 * df[2], w2 * df[3]));
+            } else {
+                for (int c = 0; c < D; ++c) { atomicAdd(gf + c, w0 * df[c]); atomicAdd(gf + D + c, w1 * df[c]); atomicAdd(gf + 2 * D + c, w2 * df[c]); }
+            }
+        }
+        if (g_xy) {
+            const float* xy = fxy + (size_t)f * 6;
+            float ax = xy[0], ay = xy[1], bx = xy[2], by = xy[3], cx = xy[4], cy = xy[5];
+            float m = bx - ax, pp = by - ay, n = cx - ax, qq = cy - ay, s = px - ax, t = py - ay;
+            float k1 = s * qq - n * t, k2 = m * t - s * pp, k3 = m * qq - n * pp;
+            float inv = 1.f / (k3 + eps);
+            float a1 = gw1 - gw0, a2 = gw2 - gw0;
+            float gk1 = a1 * inv, gk2 = a2 * inv, gk3 = -(a1 * k1 + a2 * k2) * inv * inv;
+            float g_s = gk1 * qq - gk2 * pp, g_t = -gk1 * n + gk2 * m;
+            float g_m = gk2 * t + gk3 * qq, g_pp = -gk2 * s - gk3 * n, g_n = -gk1 * t - gk3 * pp, g_q = gk1 * s + gk3 * m;
+            float2* gx2 = reinterpret_cast<float2*>(g_xy + ((size_t)b * F + f) * 6);
+            atomicAdd(gx2 + 0, make_float2(-(g_m + g_n + g_s), -(g_pp + g_q + g_t)));
+            atomicAdd(gx2 + 1, make_float2(g_m, g_pp));
+            atomicAdd(gx2 + 2, make_float2(g_n, g_q));
         }
     }
 }
@@ -306,17 +486,12 @@ extern "C" size_t dtb_sparse_render_workspace(int B, int P, int F, int R, long l
            2 * align_up(n * 4, 256) + scan_workspace_bytes((size_t)B * F) + scan_workspace_bytes(cells) + sort_workspace_bytes(n) + 2048;
 }
 
-// pixel_coords (B,P,2), render_ranges (B,P,2), face_z (B,F,3), face_xy (B,F,3,2), face_feat (B,F,3,D) ->
-// out_feat (B,P,K,D) f32, out_idx (B,P,K) i64.  R: cells per axis of the face-binning grid (<=0: 64);
-// pair_capacity: room for (cell, face) pairs (<=0: 8 per face); *overflow (device int) is set if it was too small.
-extern "C" int dtb_sparse_render_forward(const float* pixel_coords, const float* render_ranges, const float* face_z, const float* face_xy,
-                                         const float* face_feat, int B, int P, int F, int D, int K, float eps, int R, long long pair_capacity,
-                                         float* out_feat, long long* out_idx, int32_t* overflow, void* workspace, size_t workspace_bytes,
-                                         void* stream) {
-    if (B == 0 || P == 0 || K == 0) return DTB_OK;
-    DTB_REQUIRE(pixel_coords && render_ranges && out_feat && out_idx && overflow && D > 0, "sparse_render_forward: bad argument");
-    DTB_REQUIRE(K <= 1024, "sparse_render_forward: K=%d > 1024 not supported", K);
-    cudaStream_t st = (cudaStream_t)stream;
+struct RdBinning { unsigned* bbox; unsigned* cstart; unsigned* cend; unsigned* faces; int R; };
+
+// carve the binning arrays out of the workspace (same layout for forward and for a backward that reuses them) and, when
+// `build` is set, bin the faces: (cell, face) pairs sorted by cell then face id
+static int rd_binning(const float* pixel_coords, const float* face_xy, int B, int P, int F, int R, long long pair_capacity, int32_t* overflow,
+                      void* workspace, size_t workspace_bytes, bool build, cudaStream_t st, RdBinning& out) {
     if (R <= 0) R = 64;
     if (pair_capacity <= 0) pair_capacity = (long long)B * F * 8;
     size_t cells = (size_t)B * R * R, cap = (size_t)pair_capacity;
@@ -332,6 +507,8 @@ extern "C" int dtb_sparse_render_forward(const float* pixel_coords, const float*
     void* sws1 = ws.take<char>(sb1); void* sws2 = ws.take<char>(sb2); void* sows = ws.take<char>(sob);
     unsigned* total = ws.take<unsigned>(1);
     if (!ws.ok || !workspace) { set_error("sparse_render: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return DTB_EWORKSPACE; }
+    out.bbox = bbox; out.cstart = cstart; out.cend = cend; out.faces = v1; out.R = R;
+    if (!build) return DTB_OK;
     rd_init_kernel<<<cdiv(B * 4, 64), 64, 0, st>>>(bbox, B);
     dim3 gp(min(cdiv(P, 256), 128), B);
     rd_bbox_kernel<<<gp, 256, 0, st>>>(pixel_coords, P, bbox);
@@ -339,7 +516,6 @@ extern "C" int dtb_sparse_render_forward(const float* pixel_coords, const float*
     DTB_CUDA(cudaMemsetAsync(cstart, 0, cells * 4, st));
     DTB_CUDA(cudaMemsetAsync(total, 0, 4, st));
     if (F > 0) {
-        DTB_REQUIRE(face_z && face_xy && face_feat, "sparse_render_forward: null faces");
         dim3 gf(cdiv(F, 256), B);
         rd_count_kernel<<<gf, 256, 0, st>>>(face_xy, F, R, bbox, npairs);
         DTB_LAUNCH_CHECK("rd_count");
@@ -356,16 +532,80 @@ extern "C" int dtb_sparse_render_forward(const float* pixel_coords, const float*
     }
     int rc = exclusive_scan_u32(cstart, cstart, cells, nullptr, sws2, sb2, st);
     if (rc) return rc;
-    // cell_end = start + count; with a consistent sorted list, end[c] = start[c+1]; derive by shifting
     rd_cell_end_kernel<<<cdiv((long long)cells, 256), 256, 0, st>>>(cstart, total, cells, cap, cend, overflow);
     DTB_LAUNCH_CHECK("rd_cell_end");
+    return DTB_OK;
+}
+
+// pixel_coords (B,P,2), render_ranges (B,P,2), face_z (B,F,3), face_xy (B,F,3,2), face_feat (B,F,3,D) ->
+// out_feat (B,P,K,D) f32, out_idx (B,P,K) i64.  R: cells per axis of the face-binning grid (<=0: 64);
+// pair_capacity: room for (cell, face) pairs (<=0: 8 per face); *overflow (device int) is set if it was too small.
+extern "C" int dtb_sparse_render_forward(const float* pixel_coords, const float* render_ranges, const float* face_z, const float* face_xy,
+                                         const float* face_feat, int B, int P, int F, int D, int K, float eps, int R, long long pair_capacity,
+                                         float* out_feat, long long* out_idx, int32_t* overflow, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+    if (B == 0 || P == 0 || K == 0) return DTB_OK;
+    DTB_REQUIRE(pixel_coords && render_ranges && out_feat && out_idx && overflow && D > 0, "sparse_render_forward: bad argument");
+    DTB_REQUIRE(K <= 1024, "sparse_render_forward: K=%d > 1024 not supported", K);
+    DTB_REQUIRE(F == 0 || (face_z && face_xy && face_feat), "sparse_render_forward: null faces");
+    cudaStream_t st = (cudaStream_t)stream;
+    RdBinning bn;
+    int rc = rd_binning(pixel_coords, face_xy, B, P, F, R, pair_capacity, overflow, workspace, workspace_bytes, true, st, bn);
+    if (rc) return rc;
     int Kpad = rd_kpad(K);
     size_t smem = (size_t)RD_WARPS * Kpad * 16;
     if (smem > 48 * 1024) DTB_CUDA(cudaFuncSetAttribute(rd_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(cdiv(P, RD_WARPS), B);
-    rd_forward_kernel<<<grid, RD_WARPS * 32, smem, st>>>(pixel_coords, render_ranges, face_z, face_xy, face_feat, P, F, D, K, Kpad, eps, R, bbox,
-                                                         cstart, cend, v1, out_feat, out_idx);
+    rd_forward_kernel<<<grid, RD_WARPS * 32, smem, st>>>(pixel_coords, render_ranges, face_z, face_xy, face_feat, P, F, D, K, Kpad, eps, bn.R,
+                                                         bn.bbox, bn.cstart, bn.cend, bn.faces, out_feat, out_idx);
     DTB_LAUNCH_CHECK("rd_forward");
+    return DTB_OK;
+}
+
+// Fused render + front-to-back composite: out_color (B,P,D-1), out_mask (B,P,1); the workspace keeps the face binning for
+// dtb_render_composite_backward (call it with the SAME workspace, sizes, R and pair_capacity).
+extern "C" int dtb_render_composite_forward(const float* pixel_coords, const float* render_ranges, const float* face_z, const float* face_xy,
+                                            const float* face_feat, int B, int P, int F, int D, int K, float eps, int R, long long pair_capacity,
+                                            float* out_color, float* out_mask, int32_t* overflow, void* workspace, size_t workspace_bytes,
+                                            void* stream) {
+    if (B == 0 || P == 0) return DTB_OK;
+    DTB_REQUIRE(pixel_coords && render_ranges && out_color && out_mask && overflow, "render_composite_forward: null argument");
+    DTB_REQUIRE(D >= 2 && D <= RC_MAXD, "render_composite_forward: D=%d must be in [2, %d] (alpha + colour channels)", D, RC_MAXD);
+    DTB_REQUIRE(K >= 1 && K <= 1024, "render_composite_forward: K=%d out of range", K);
+    DTB_REQUIRE(F == 0 || (face_z && face_xy && face_feat), "render_composite_forward: null faces");
+    cudaStream_t st = (cudaStream_t)stream;
+    RdBinning bn;
+    int rc = rd_binning(pixel_coords, face_xy, B, P, F, R, pair_capacity, overflow, workspace, workspace_bytes, true, st, bn);
+    if (rc) return rc;
+    int Kpad = rd_kpad(K);
+    size_t smem = (size_t)RD_WARPS * Kpad * 16;
+    if (smem > 48 * 1024) DTB_CUDA(cudaFuncSetAttribute(rc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(P, RD_WARPS), B);
+    rc_forward_kernel<<<grid, RD_WARPS * 32, smem, st>>>(pixel_coords, render_ranges, face_z, face_xy, face_feat, P, F, D, K, Kpad, eps, bn.R,
+                                                         bn.bbox, bn.cstart, bn.cend, bn.faces, out_color, out_mask);
+    DTB_LAUNCH_CHECK("rc_forward");
+    return DTB_OK;
+}
+
+// g_color (B,P,D-1), g_mask (B,P,1) -> ACCUMULATES into g_xy (B,F,3,2) and g_feat (B,F,3,D) (either may be NULL)
+extern "C" int dtb_render_composite_backward(const float* pixel_coords, const float* render_ranges, const float* face_z, const float* face_xy,
+                                             const float* face_feat, const float* g_color, const float* g_mask, int B, int P, int F, int D, int K,
+                                             float eps, int R, long long pair_capacity, float* g_xy, float* g_feat, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
+    if (B == 0 || P == 0 || F == 0) return DTB_OK;
+    DTB_REQUIRE(pixel_coords && render_ranges && face_z && face_xy && face_feat && g_color && g_mask, "render_composite_backward: null argument");
+    DTB_REQUIRE(D >= 2 && D <= RC_MAXD && K >= 1 && K <= 1024, "render_composite_backward: D / K out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    RdBinning bn;
+    int rc = rd_binning(pixel_coords, face_xy, B, P, F, R, pair_capacity, nullptr, workspace, workspace_bytes, false, st, bn);
+    if (rc) return rc;
+    int Kpad = rd_kpad(K);
+    size_t smem = (size_t)RD_WARPS * Kpad * 24;
+    if (smem > 48 * 1024) DTB_CUDA(cudaFuncSetAttribute(rc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(P, RD_WARPS), B);
+    rc_backward_kernel<<<grid, RD_WARPS * 32, smem, st>>>(pixel_coords, render_ranges, face_z, face_xy, face_feat, P, F, D, K, Kpad, eps, bn.R,
+                                                          bn.bbox, bn.cstart, bn.cend, bn.faces, g_color, g_mask, g_xy, g_feat);
+    DTB_LAUNCH_CHECK("rc_backward");
     return DTB_OK;
 }
 

@@ -24,6 +24,8 @@ def _render_sigs(lib, sig):
     sig("dtb_sparse_render_workspace", sz, i, i, i, i, ll)
     sig("dtb_sparse_render_forward", i, vp, vp, vp, vp, vp, i, i, i, i, i, f, i, ll, vp, vp, vp, vp, sz, vp)
     sig("dtb_sparse_render_backward", i, vp, vp, vp, vp, vp, i, i, i, i, i, f, vp, vp, vp)
+    sig("dtb_render_composite_forward", i, vp, vp, vp, vp, vp, i, i, i, i, i, f, i, ll, vp, vp, vp, vp, sz, vp)
+    sig("dtb_render_composite_backward", i, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, f, i, ll, vp, vp, vp, sz, vp)
     sig("dtb_check_sign_workspace", sz, i, i, i)
     sig("dtb_check_sign", i, vp, vp, vp, i, i, i, i, i, vp, vp, sz, vp)
     sig("dtb_laplacian_forward", i, vp, vp, vp, i, i, i, vp, vp, vp, vp, vp)
@@ -81,6 +83,60 @@ def deftet_sparse_render(pixel_coords, render_ranges, face_vertices_z, face_vert
     """-> (face_features_out (B,P,knum,d), face_idx (B,P,knum) long)."""
     return _SparseRender.apply(pixel_coords, render_ranges, face_vertices_z, face_vertices_image, face_features, int(knum), float(eps),
                                int(grid_res))
+
+
+class _RenderComposite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pixel_coords, render_ranges, face_vertices_z, face_vertices_image, face_features, knum, eps, grid_res):
+        _lib.require_cuda(pixel_coords, face_vertices_image)
+        pix, rng = _f32c(pixel_coords), _f32c(render_ranges)
+        fz, fxy, ff = _f32c(face_vertices_z), _f32c(face_vertices_image), _f32c(face_features)
+        B, P = pix.shape[0], pix.shape[1]
+        F, D = fz.shape[1], ff.shape[-1]
+        dev = pix.device
+        L = _lib.lib()
+        color = torch.empty(B, P, D - 1, device=dev)
+        mask = torch.empty(B, P, 1, device=dev)
+        overflow = torch.zeros(1, device=dev, dtype=torch.int32)
+        cap = max(B * F * 8, 1024)
+        with torch.cuda.device(dev):
+            for _ in range(6):
+                wsz = L.dtb_sparse_render_workspace(B, P, F, grid_res, cap)
+                ws = torch.empty(wsz, device=dev, dtype=torch.uint8)
+                _lib.check(L.dtb_render_composite_forward(_lib.ptr(pix), _lib.ptr(rng), _lib.ptr(fz), _lib.ptr(fxy), _lib.ptr(ff), B, P, F, D,
+                                                          knum, eps, grid_res, cap, _lib.ptr(color), _lib.ptr(mask), _lib.ptr(overflow),
+                                                          _lib.ptr(ws), wsz, _lib.stream_ptr()), "dtb_render_composite_forward")
+                if int(overflow.item()) == 0:
+                    break
+                cap *= 4
+            else:
+                raise _lib.DeftetB200Error("render_composite: face-binning capacity exceeded")
+        ctx.save_for_backward(pix, rng, fz, fxy, ff, ws)
+        ctx.cfg = (knum, eps, grid_res, cap)
+        return color, mask
+
+    @staticmethod
+    def backward(ctx, g_color, g_mask):
+        pix, rng, fz, fxy, ff, ws = ctx.saved_tensors
+        knum, eps, grid_res, cap = ctx.cfg
+        B, P = pix.shape[0], pix.shape[1]
+        F, D = fz.shape[1], ff.shape[-1]
+        g_color, g_mask = _f32c(g_color), _f32c(g_mask)
+        g_xy = torch.zeros_like(fxy) if ctx.needs_input_grad[3] else None
+        g_ff = torch.zeros_like(ff) if ctx.needs_input_grad[4] else None
+        with torch.cuda.device(pix.device):
+            _lib.check(_lib.lib().dtb_render_composite_backward(_lib.ptr(pix), _lib.ptr(rng), _lib.ptr(fz), _lib.ptr(fxy), _lib.ptr(ff),
+                                                                _lib.ptr(g_color), _lib.ptr(g_mask), B, P, F, D, knum, eps, grid_res, cap,
+                                                                _lib.ptr(g_xy), _lib.ptr(g_ff), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                       "dtb_render_composite_backward")
+        return None, None, None, g_xy, g_ff, None, None, None
+
+
+def render_composite(pixel_coords, render_ranges, face_vertices_z, face_vertices_image, face_features, knum=300, eps=1e-8, grid_res=0):
+    """Fused ``deftet_sparse_render`` + ``peel2mask`` (5_rendereq/deftetrneder.py:31-64,97-113): -> (colour (B,P,d-1), mask (B,P,1))
+    with white background, never materialising the (B,P,K,d) tensor.  face_features channel 0 is the opacity."""
+    return _RenderComposite.apply(pixel_coords, render_ranges, face_vertices_z, face_vertices_image, face_features, int(knum), float(eps),
+                                  int(grid_res))
 
 
 def check_sign(verts, faces, points, hash_resolution=512):

@@ -244,6 +244,21 @@ int dtb_sparse_render_backward(const float* pixel_coords, const float* face_xy, 
                                const float* g_out, int B, int P, int F, int D, int K, float eps, float* g_xy, float* g_feat,
                                void* stream);
 
+/* Fused render + composite fast path: rendermeshcolor's deftet_sparse_render -> peel2mask chain
+ * (diff_render/diftet_6_subdiv/5_rendereq/deftetrneder.py:31-64,97-113) without the (B,P,K,D) intermediate.
+ * Feature channel 0 is the opacity: alpha_k = clamp(f_k[0], 1e-10, 1-1e-10), vis_k = alpha_k prod_{i<k}(1-alpha_i) over the K
+ * depth-sorted slots (void slots: f = 0); out_color (B,P,D-1) = sum_k vis_k c_k + (1 - sum_k vis_k), out_mask (B,P,1) = sum_k vis_k.
+ * 2 <= D <= 8.  backward recollects the hits with the face binning the forward left in `workspace` (pass the same workspace,
+ * sizes, R and pair_capacity) and ACCUMULATES into g_xy (B,F,3,2) / g_feat (B,F,3,D). */
+int dtb_render_composite_forward(const float* pixel_coords, const float* render_ranges, const float* face_z, const float* face_xy,
+                                 const float* face_feat, int B, int P, int F, int D, int K, float eps, int R, long long pair_capacity,
+                                 float* out_color, float* out_mask, int32_t* overflow, void* workspace, size_t workspace_bytes,
+                                 void* stream);
+int dtb_render_composite_backward(const float* pixel_coords, const float* render_ranges, const float* face_z, const float* face_xy,
+                                  const float* face_feat, const float* g_color, const float* g_mask, int B, int P, int F, int D, int K,
+                                  float eps, int R, long long pair_capacity, float* g_xy, float* g_feat, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
 /* ---- A16: inside/outside labels (stand-in for kal.ops.mesh.check_sign, layers/DefTet/deftet.py:46) ------------
  * verts (B,n,3), faces (m,3) i32 shared by the batch, points (B,p,3) -> out (B,p) u8, 1 = inside (+z ray parity,
  * half-open edge rule; oracle/render_oracle.c).  R = kaolin's hash_resolution (xy grid; <=0: 256, max 1024).

@@ -90,3 +90,14 @@ def surface_losses(pos_bxvx3, boundary_list, gt_bxsx3, u_list, v_list):
         ch.append(chamfer(q, gt_bxsx3[b:b + 1]).mean(dim=-1))
         an.append(point_mesh_distance(gt_bxsx3[b:b + 1], surf).mean(dim=-1).mean(dim=-1))
     return torch.cat(ch), torch.cat(an), torch.cat(nl)
+
+
+def peel2mask(ims_bxpxkxd):
+    """Front-to-back compositing of the K depth-sorted slots (5_rendereq/deftetrneder.py:31-64), white background."""
+    mask = torch.clamp(ims_bxpxkxd[..., :1], 1e-10, 1.0 - 1e-10)
+    color = ims_bxpxkxd[..., 1:]
+    shift = torch.nn.functional.pad(1 - mask[:, :, :-1, :], pad=(0, 0, 1, 0), mode="constant", value=1)
+    vis = mask * torch.cumprod(shift, dim=2)
+    xcolor = (color * vis).sum(dim=2)
+    xvis = vis.sum(2)
+    return xcolor + (1.0 - xvis), xvis

@@ -128,3 +128,31 @@ def test_laplacian_matches_sparse_mm():
     (ref * torch.tensor([1.0, 2.0], dtype=torch.float64)).sum().backward()
     assert rel_err(loss, ref.detach()) < 1e-5
     assert rel_err(doff.grad, roff.grad) < 1e-5
+
+
+@pytest.mark.parametrize("K", [8, 40])
+def test_render_composite_fused_matches_render_then_peel2mask(K):
+    """Fused fast path == deftet_sparse_render followed by the reference's peel2mask (forward and gradients)."""
+    from deftet_b200 import render
+    from oracle import surface as orc_s
+    B, F, P, D = 1, 1500, 600, 4
+    pix, rng, z, xy, feat = _render_scene(B, F, P, D, 17)
+    feat = feat * 0.6                                            # opacities spread over (0, 0.6): several layers stay visible
+    feat[0, :50, :, 0] = 1.5                                     # some opacities beyond the clamp
+    feat[0, 50:100, :, 0] = -0.2
+    gen = torch.Generator().manual_seed(2)
+    gcol, gmask = torch.randn(B, P, D - 1, generator=gen), torch.randn(B, P, 1, generator=gen)
+    # unfused chain on the GPU kernels already validated above, composited by torch (float64)
+    rxy = xy.cuda().requires_grad_(True)
+    rfeat = feat.cuda().requires_grad_(True)
+    ims, _ = render.deftet_sparse_render(pix.cuda(), rng.cuda(), z.cuda(), rxy, rfeat, knum=K)
+    rc, rm = orc_s.peel2mask(ims.double())
+    ((rc * gcol.cuda().double()).sum() + (rm * gmask.cuda().double()).sum()).backward()
+    dxy = xy.cuda().requires_grad_(True)
+    dfeat = feat.cuda().requires_grad_(True)
+    color, mask = render.render_composite(pix.cuda(), rng.cuda(), z.cuda(), dxy, dfeat, knum=K)
+    assert color.shape == (B, P, D - 1) and mask.shape == (B, P, 1)
+    ((color * gcol.cuda()).sum() + (mask * gmask.cuda()).sum()).backward()
+    assert rel_err(color, rc.detach()) < 1e-5 and rel_err(mask, rm.detach()) < 1e-5
+    assert rel_err(dfeat.grad, rfeat.grad) < 1e-4
+    assert rel_err(dxy.grad, rxy.grad) < 1e-4
