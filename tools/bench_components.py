@@ -113,6 +113,32 @@ def main():
         emit(row="A15 deftet_sparse_render fwd", pixels=pix.shape[1], faces=F, K=K, hits_per_pixel=hits / pix.shape[1], ms=med, algorithmic_bytes=by,
              hbm_frac=by / (med * 1e-3) / 1e9 / peak, max_slots_used=int((idx >= 0).sum(-1).max()))
         del out, idx
+    # fused render + composite (never writes the (P,K,D) tensor), forward and forward+backward
+    fxy_g = fxy.clone().requires_grad_(True)
+    feat_g = feat.clone().requires_grad_(True)
+    for K in ((64,) if a.quick else (64, 300)):
+        with torch.no_grad():
+            med, _ = timeit(lambda: render.render_composite(pix, rng, fz, fxy, feat, knum=K), 3, 1, flush)
+        by = pix.shape[1] * (8 + 8 + 16) + F * (12 + 24 + 48)
+        emit(row="A15 fused render_composite fwd", pixels=pix.shape[1], faces=F, K=K, ms=med, algorithmic_bytes=by,
+             hbm_frac=by / (med * 1e-3) / 1e9 / peak)
+
+        def fb():
+            fxy_g.grad = None; feat_g.grad = None
+            c, m = render.render_composite(pix, rng, fz, fxy_g, feat_g, knum=K)
+            (c.sum() + m.sum()).backward()
+        med, _ = timeit(fb, 3, 1, flush)
+        emit(row="A15 fused render_composite fwd+bwd", pixels=pix.shape[1], faces=F, K=K, ms=med)
+
+        def fb_unfused():
+            fxy_g.grad = None; feat_g.grad = None
+            ims, _ = render.deftet_sparse_render(pix, rng, fz, fxy_g, feat_g, knum=K)
+            m = torch.clamp(ims[..., :1], 1e-10, 1 - 1e-10)
+            vis = m * torch.cumprod(torch.nn.functional.pad(1 - m[:, :, :-1], (0, 0, 1, 0), value=1.0), dim=2)
+            ((ims[..., 1:] * vis).sum(2).sum() + vis.sum()).backward()
+        if K <= 64:
+            med, _ = timeit(fb_unfused, 3, 1, flush)
+            emit(row="A15 drop-in deftet_sparse_render + torch peel2mask fwd+bwd", pixels=pix.shape[1], faces=F, K=K, ms=med)
     # ---- A16 check_sign: sphere mesh, T centroids -----------------------------------------------------------------------------
     from tests.test_gpu_render import _icosphere
     v, f = _icosphere(5)
