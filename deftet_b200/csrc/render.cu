@@ -537,6 +537,37 @@ static int rd_binning(const float* pixel_coords, const float* face_xy, int B, in
     return DTB_OK;
 }
 
+// Number of (cell, face) pairs the binning will produce for these inputs: written to *n_pairs (device int64-free: u32).
+// Lets the caller size pair_capacity exactly instead of guessing (one tiny kernel sequence + one host read).
+__global__ void rd_sum_kernel(const unsigned* __restrict__ npairs, size_t n, unsigned* __restrict__ total) {
+    unsigned s = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += npairs[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, s);
+}
+extern "C" int dtb_sparse_render_pair_count(const float* pixel_coords, const float* face_xy, int B, int P, int F, int R, unsigned* n_pairs,
+                                            void* workspace, size_t workspace_bytes, void* stream) {
+    DTB_REQUIRE(n_pairs != nullptr, "sparse_render_pair_count: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    DTB_CUDA(cudaMemsetAsync(n_pairs, 0, sizeof(unsigned), st));
+    if (B == 0 || P == 0 || F == 0) return DTB_OK;
+    DTB_REQUIRE(pixel_coords && face_xy, "sparse_render_pair_count: null argument");
+    if (R <= 0) R = 64;
+    Workspace ws(workspace, workspace_bytes);
+    unsigned* bbox = ws.take<unsigned>((size_t)B * 4);
+    unsigned* npairs = ws.take<unsigned>((size_t)B * F);
+    if (!ws.ok || !workspace) { set_error("sparse_render_pair_count: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return DTB_EWORKSPACE; }
+    rd_init_kernel<<<cdiv(B * 4, 64), 64, 0, st>>>(bbox, B);
+    dim3 gp(min(cdiv(P, 256), 128), B);
+    rd_bbox_kernel<<<gp, 256, 0, st>>>(pixel_coords, P, bbox);
+    dim3 gf(cdiv(F, 256), B);
+    rd_count_kernel<<<gf, 256, 0, st>>>(face_xy, F, R, bbox, npairs);
+    rd_sum_kernel<<<min(cdiv((long long)B * F, 256), 256), 256, 0, st>>>(npairs, (size_t)B * F, n_pairs);
+    DTB_LAUNCH_CHECK("rd_pair_count");
+    return DTB_OK;
+}
+
 // pixel_coords (B,P,2), render_ranges (B,P,2), face_z (B,F,3), face_xy (B,F,3,2), face_feat (B,F,3,D) ->
 // out_feat (B,P,K,D) f32, out_idx (B,P,K) i64.  R: cells per axis of the face-binning grid (<=0: 64);
 // pair_capacity: room for (cell, face) pairs (<=0: 8 per face); *overflow (device int) is set if it was too small.

@@ -22,6 +22,7 @@ from .search import _f32c
 def _render_sigs(lib, sig):
     vp, i, sz, ll, f = C.c_void_p, C.c_int, C.c_size_t, C.c_longlong, C.c_float
     sig("dtb_sparse_render_workspace", sz, i, i, i, i, ll)
+    sig("dtb_sparse_render_pair_count", i, vp, vp, i, i, i, i, vp, vp, sz, vp)
     sig("dtb_sparse_render_forward", i, vp, vp, vp, vp, vp, i, i, i, i, i, f, i, ll, vp, vp, vp, vp, sz, vp)
     sig("dtb_sparse_render_backward", i, vp, vp, vp, vp, vp, i, i, i, i, i, f, vp, vp, vp)
     sig("dtb_render_composite_forward", i, vp, vp, vp, vp, vp, i, i, i, i, i, f, i, ll, vp, vp, vp, vp, sz, vp)
@@ -30,6 +31,17 @@ def _render_sigs(lib, sig):
     sig("dtb_check_sign", i, vp, vp, vp, i, i, i, i, i, vp, vp, sz, vp)
     sig("dtb_laplacian_forward", i, vp, vp, vp, i, i, i, vp, vp, vp, vp, vp)
     sig("dtb_laplacian_backward", i, vp, vp, vp, vp, vp, i, i, vp, vp)
+
+
+def _pair_capacity(pix, fxy, grid_res):
+    """Exact (cell, face) pair count of the binning (one small kernel sequence + one host read)."""
+    B, P, F = pix.shape[0], pix.shape[1], fxy.shape[1]
+    n = torch.zeros(1, device=pix.device, dtype=torch.int32)
+    wsz = (4 * B + B * F) * 4 + 1024
+    ws = torch.empty(wsz, device=pix.device, dtype=torch.uint8)
+    _lib.check(_lib.lib().dtb_sparse_render_pair_count(_lib.ptr(pix), _lib.ptr(fxy), B, P, F, grid_res, _lib.ptr(n), _lib.ptr(ws), wsz,
+                                                       _lib.stream_ptr()), "dtb_sparse_render_pair_count")
+    return max(int(n.item()), 1024)
 
 
 class _SparseRender(torch.autograd.Function):
@@ -45,9 +57,9 @@ class _SparseRender(torch.autograd.Function):
         out = torch.empty(B, P, knum, D, device=dev)
         idx = torch.empty(B, P, knum, device=dev, dtype=torch.int64)
         overflow = torch.zeros(1, device=dev, dtype=torch.int32)
-        cap = max(B * F * 8, 1024)
         with torch.cuda.device(dev):
-            for _ in range(6):
+            cap = _pair_capacity(pix, fxy, grid_res)
+            for _ in range(2):
                 wsz = L.dtb_sparse_render_workspace(B, P, F, grid_res, cap)
                 ws = torch.empty(wsz, device=dev, dtype=torch.uint8)
                 _lib.check(L.dtb_sparse_render_forward(_lib.ptr(pix), _lib.ptr(rng), _lib.ptr(fz), _lib.ptr(fxy), _lib.ptr(ff), B, P, F, D,
@@ -98,9 +110,9 @@ class _RenderComposite(torch.autograd.Function):
         color = torch.empty(B, P, D - 1, device=dev)
         mask = torch.empty(B, P, 1, device=dev)
         overflow = torch.zeros(1, device=dev, dtype=torch.int32)
-        cap = max(B * F * 8, 1024)
         with torch.cuda.device(dev):
-            for _ in range(6):
+            cap = _pair_capacity(pix, fxy, grid_res)
+            for _ in range(2):
                 wsz = L.dtb_sparse_render_workspace(B, P, F, grid_res, cap)
                 ws = torch.empty(wsz, device=dev, dtype=torch.uint8)
                 _lib.check(L.dtb_render_composite_forward(_lib.ptr(pix), _lib.ptr(rng), _lib.ptr(fz), _lib.ptr(fxy), _lib.ptr(ff), B, P, F, D,

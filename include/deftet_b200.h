@@ -236,6 +236,9 @@ int dtb_host_colaps_v(const float* point_p, int32_t* map_array_p, int32_t* inver
  * face); *overflow (device int32) is set to 1 when it was too small (results are then invalid: retry larger).
  * backward ACCUMULATES into g_xy (B,F,3,2) and g_feat (B,F,3,D); no gradient to z or the pixel. */
 size_t dtb_sparse_render_workspace(int B, int P, int F, int R, long long pair_capacity);
+/* exact number of (cell, face) pairs for these inputs -> *n_pairs (device u32); workspace >= (4*B + B*F)*4 + 512 bytes */
+int dtb_sparse_render_pair_count(const float* pixel_coords, const float* face_xy, int B, int P, int F, int R, unsigned* n_pairs,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 int dtb_sparse_render_forward(const float* pixel_coords, const float* render_ranges, const float* face_z, const float* face_xy,
                               const float* face_feat, int B, int P, int F, int D, int K, float eps, int R, long long pair_capacity,
                               float* out_feat, long long* out_idx, int32_t* overflow, void* workspace, size_t workspace_bytes,

@@ -28,7 +28,7 @@ pix = (torch.stack([xs, ys], -1).reshape(1, -1, 2) * 1000).contiguous()
 rng = torch.tensor([-1000.0, 0.0], device=dev).reshape(1, 1, 2).expand(1, pix.shape[1], 2).contiguous()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for K in (64, 300):
-    for R in (64, 128, 192, 256, 384, 512):
+    for R in (48, 64, 96, 128, 192, 256):
         with torch.no_grad():
             med, _ = timeit(lambda: render.deftet_sparse_render(pix, rng, fz, fxy, feat, knum=K, grid_res=R), 3, 1, flush)
         print("K=%3d R=%3d fwd %.3f ms" % (K, R, med))
@@ -36,3 +36,7 @@ out, idx = render.deftet_sparse_render(pix, rng, fz, fxy, feat, knum=64, grid_re
 gout = torch.rand_like(out)
 med, _ = timeit(lambda: torch.autograd.grad((out * gout).sum(), (fxy, feat), retain_graph=True), 3, 1, flush)
 print("K=64 backward (incl. mul/sum) %.3f ms" % med)
+for R in (64, 128, 192):
+    with torch.no_grad():
+        med, _ = timeit(lambda: render.render_composite(pix, rng, fz, fxy, feat, knum=300, grid_res=R), 3, 1, flush)
+    print("fused K=300 R=%3d fwd %.3f ms" % (R, med))
