@@ -111,7 +111,10 @@ __device__ __forceinline__ void face_precompute(const float* t, FacePre& f) {
     float r2[3] = {xsub(f.c[0], f.a[0]), xsub(f.c[1], f.a[1]), xsub(f.c[2], f.a[2])};
     float n[3] = {xsub(xmul(r1[1], r2[2]), xmul(r1[2], r2[1])), xsub(xmul(r1[2], r2[0]), xmul(r1[0], r2[2])),
                   xsub(xmul(r1[0], r2[1]), xmul(r1[1], r2[0]))};
-    float len = div_nz(xsqrt(xadd(xadd(xmul(n[0], n[0]), xmul(n[1], n[1])), xmul(n[2], n[2]))));
+    float raw_len = xsqrt(xadd(xadd(xmul(n[0], n[0]), xmul(n[1], n[1])), xmul(n[2], n[2])));
+    float len = div_nz(raw_len);
+    f.pad[0] = raw_len;                  // |cross| = twice the area: used to flag faces too small for geometric pruning
+    f.pad[1] = 0.f;
     f.n[0] = xdiv(n[0], len); f.n[1] = xdiv(n[1], len); f.n[2] = xdiv(n[2], len);
     f.na = xdot(f.n, f.a);
     f.bc1 = xsub(f.b[1], f.c[1]); f.cb0 = xsub(f.c[0], f.b[0]); f.ac0 = xsub(f.a[0], f.c[0]); f.ca1 = xsub(f.c[1], f.a[1]);
@@ -159,7 +162,6 @@ __global__ void __launch_bounds__(256) face_stats_kernel(const float* __restrict
         if (pre) {                                   // query-independent half of the distance, once per face
             FacePre fp;
             face_precompute(t, fp);
-            fp.pad[0] = fp.pad[1] = 0.f;
             const float4* src = reinterpret_cast<const float4*>(&fp);
             float4* dst = pre + ((size_t)b * Fmax + f) * 8;
 #pragma unroll
@@ -174,8 +176,14 @@ __global__ void __launch_bounds__(256) face_stats_kernel(const float* __restrict
         float e1[3] = {t[3] - t[0], t[4] - t[1], t[5] - t[2]}, e2[3] = {t[6] - t[0], t[7] - t[1], t[8] - t[2]};
         float nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
         float nn = sqrtf(nx * nx + ny * ny + nz * nz);
-        // xy-projection unreliable (or not a finite triangle): never prune this face geometrically
-        bool unreliable = !(fabsf(nz) > 1e-3f * nn) || !(r == r) || !(nn == nn);
+        // Never prune a face geometrically when the reference distance can deviate from the Euclidean one by more than the
+        // pruning slack: xy-projection unreliable (normal almost horizontal), not a finite triangle, or so small that the
+        // reference's absolute epsilons (cuda_divide_non_zero: len + 1e-10, |BA|^2 + 1e-10) are no longer negligible.
+        float l1 = e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2], l2 = e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2];
+        float e3x = t[6] - t[3], e3y = t[7] - t[4], e3z = t[8] - t[5];
+        float l3 = e3x * e3x + e3y * e3y + e3z * e3z;
+        bool tiny = !(nn > 1e-5f) || !(fminf(l1, fminf(l2, l3)) > 1e-5f);
+        bool unreliable = !(fabsf(nz) > 1e-3f * nn) || !(r == r) || !(nn == nn) || tiny;
         if (unreliable) {
             int k = atomicAdd(n_always + b, 1);
             if (k < always_cap) always[(size_t)b * always_cap + k] = f;
@@ -359,7 +367,8 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
                     const FacePre& fp = *reinterpret_cast<const FacePre*>(dst);
                     // same reliability rule as face_stats_kernel (unit normal here): unreliable or invisible faces may
                     // have a reference distance larger than the distance to their centroid
-                    s_rel[k] = (fp.k3 != 0.f && fabsf(fp.n[2]) > 2e-3f) ? 1 : 0;
+                    s_rel[k] = (fp.k3 != 0.f && fabsf(fp.n[2]) > 2e-3f && fminf(fp.den_ab, fminf(fp.den_bc, fp.den_ac)) > 1.0001e-5f &&
+                                fp.pad[0] > 1e-5f) ? 1 : 0;
                 }
             }
             __syncthreads();
