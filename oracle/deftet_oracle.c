@@ -5,6 +5,8 @@
  * operator (build with -ffp-contract=off; never -ffast-math).  Every function takes an [i0, i1) range of its outer (per point / per face) loop so that
  * the Python wrapper can spread it over host threads (ctypes releases the GIL; libgomp is not in this
  * image); results do not depend on the split.  Nothing in deftet_b200/ links or loads this file.
+ * PINNED: checked bit for bit against the reference's own __host__ __device__ functions compiled for the host
+ * (oracle/build_ref_kernels.sh -> oracle/_ref/kernels/*.so; tests/test_golden.py), except the trivial A2 body.
  *
  *   orc_point_in_tet            layers/DefTet/check_condition_tetrahedron_base/check_condition_tet_for.cu:105-189
  *   orc_nearest_neighbor        layers/nearest_neighbor/nearest_neighbor_cuda.cu:17-55

@@ -165,3 +165,47 @@ def check_sign(verts, faces, points, threads=None):
     _split(lambda a, b: L.orc_check_sign(_p(v), _p(f), _p(p), B, n, m, np_, _p(out), C.c_longlong(a), C.c_longlong(b)), B * np_, threads,
            min_chunk=16)
     return out.astype(bool)
+
+
+# ---- the reference's own __host__ __device__ kernel helpers compiled for the host (oracle/build_ref_kernels.sh) ----
+def ref_kernel_lib(name):
+    path = os.path.join(HERE, "_ref", "kernels", name + ".so")
+    return C.CDLL(path) if os.path.exists(path) else None
+
+
+def ref_point_in_tet(tet_bxfx4x3, pts_bxnx3):
+    L = ref_kernel_lib("point_in_tet")
+    tet, pts = _f32(tet_bxfx4x3), _f32(pts_bxnx3)
+    B, T, P = tet.shape[0], tet.shape[1], pts.shape[1]
+    out = np.full((B, P, 1), -1.0, dtype=np.float32)
+    L.ref_point_in_tet(_p(tet), _p(pts), _p(out), B, P, T)
+    return out
+
+
+def ref_point_face_distance(pts, faces):
+    L = ref_kernel_lib("face_distance_fwd")
+    pts, faces = _f32(pts), _f32(faces)
+    B, P, F = pts.shape[0], pts.shape[1], faces.shape[1]
+    nf = _f32(np.full(B, F))
+    d = np.zeros((B, P, 1), dtype=np.float32)
+    f = np.zeros((B, P, 1), dtype=np.float32)
+    L.ref_point_face_distance(_p(pts), _p(faces), _p(nf), _p(d), _p(f), B, P, F)
+    return d, f
+
+
+def ref_point_face_distance_bwd(pts, faces, closest_f, dl_dd):
+    L = ref_kernel_lib("face_distance_bwd")
+    pts, faces, cf, g = _f32(pts), _f32(faces), _f32(closest_f), _f32(dl_dd)
+    B, P, F = pts.shape[0], pts.shape[1], faces.shape[1]
+    out = np.zeros((B, F, 3, 3), dtype=np.float32)
+    L.ref_point_face_distance_bwd(_p(pts), _p(faces), _p(cf), _p(g), _p(out), B, P, F)
+    return out
+
+
+def ref_face_adjacency(face_fx3x3, n_max_nei=30):
+    L = ref_kernel_lib("face_adj")
+    face = _f32(face_fx3x3)
+    F = face.shape[0]
+    adj = np.full((F, n_max_nei), -1.0, dtype=np.float32)
+    L.ref_face_adjacency(_p(face), _p(adj), F, n_max_nei)
+    return adj

@@ -91,3 +91,44 @@ def test_grid_generator_properties():
         assert np.array_equal(v2, g.vertices) and mask.shape == (g.n_vert, 3)
     g2 = acute_lattice_grid(8)
     assert np.array_equal(g2.tets, acute_lattice_grid(8).tets)
+
+
+@pytest.mark.skipif(native.ref_kernel_lib("point_in_tet") is None, reason="oracle/_ref/kernels not built (needs /root/reference + nvcc at build time)")
+def test_c_restatement_matches_reference_device_functions_compiled_for_host():
+    """The CUDA-only reference kernels keep their per-element math in `__host__ __device__` templates; oracle/build_ref_kernels.sh
+    compiles exactly those functions for the CPU.  The C restatement (oracle/deftet_oracle.c) must agree with them bit for bit."""
+    from oracle import surface as orc_s
+    from tests.util import sphere_occupancy
+    g, pos, tet = deformed_grid(8, 2, seed=21)
+    gen = torch.Generator().manual_seed(0)
+    pts = (torch.rand(2, 1500, 3, generator=gen) - 0.5) * 1.05
+    pts[0, :100] = pos[0, :100]
+    soup = orc_e.gather_tets(pos, tet).numpy()
+    assert np.array_equal(native.point_in_tet(soup, pts.numpy()), native.ref_point_in_tet(soup, pts.numpy()))
+    # undeformed grid: points exactly on lattice planes / vertices
+    g0, pos0, tet0 = deformed_grid(8, 1, seed=0, amp=0.0)
+    p0 = torch.round(pts[:1] * 8) / 8
+    soup0 = orc_e.gather_tets(pos0, tet0).numpy()
+    assert np.array_equal(native.point_in_tet(soup0, p0.numpy()), native.ref_point_in_tet(soup0, p0.numpy()))
+    # A4 forward / backward on a boundary-face soup (deformed and undeformed: k3 == 0 faces) + random soup
+    f3, ft2, _, _ = orc_b.tet_to_face(g.n_vert, g.tets)
+    for pp, tt in ((pos, tet), (pos0, tet0)):
+        occ = sphere_occupancy(pp[:1], tt, [[0.0, 0.0, 0.0]], [0.3])
+        bnd = orc_s.get_boundary_index(torch.from_numpy(f3), torch.from_numpy(ft2), occ)[0]
+        faces = orc_s.gather_faces(pp[:1], bnd).numpy()
+        q = pts[:1, :800].numpy()
+        d, f = native.point_face_distance(q, faces)
+        dr, fr = native.ref_point_face_distance(q, faces)
+        assert np.array_equal(f, fr) and np.array_equal(d, dr)
+        gd = torch.rand(1, 800, 1, generator=gen).numpy()
+        assert np.array_equal(native.point_face_distance_bwd(q, faces, f, gd), native.ref_point_face_distance_bwd(q, faces, fr, gd))
+        adj, _ = native.face_adjacency(faces[0])
+        assert np.array_equal(adj, native.ref_face_adjacency(faces[0]))
+    rs = (torch.rand(1, 300, 3, 3, generator=gen) - 0.5).numpy()
+    rs[0, :20, :, 0] = rs[0, :20, :1, 0]                      # vertical faces
+    q = ((torch.rand(1, 500, 3, generator=gen) - 0.5) * 1.3).numpy()
+    d, f = native.point_face_distance(q, rs)
+    dr, fr = native.ref_point_face_distance(q, rs)
+    assert np.array_equal(f, fr) and np.array_equal(d, dr)
+    gd = torch.rand(1, 500, 1, generator=gen).numpy()
+    assert np.array_equal(native.point_face_distance_bwd(q, rs, f, gd), native.ref_point_face_distance_bwd(q, rs, fr, gd))
