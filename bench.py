@@ -185,6 +185,59 @@ def cpu_reference_step(grid, B, P, S, seed, budget_s=20.0, threads=None):
     return B * T / (t_total * 1e3), threads, desc
 
 
+# ------------------------------------------------------------------------------------------------- reference CUDA leg
+def reference_cuda_step(eng, grid, sc, Fmax, S_face, B, T):
+    """The reference's own GPU implementation of the same step on the same B200 and the same inputs: its unmodified CUDA
+    kernels (oracle/_ref/kernels_cuda, brute force: A1 O(P*T), A2 O(Q*S), A4 O(S*F_b), A5 O(F_b^2)) in the reference's
+    per-sample loop (deftet.py:89-103), and its pure-PyTorch energies + autograd on CUDA tensors (op-for-op restatement,
+    oracle/energies.py).  One timed pass after one warm-up pass of every part; a reported baseline, not the product."""
+    from oracle import energies as orc_e
+    from oracle import ref_cuda
+    from deftet_b200 import surface
+    if not ref_cuda.available():
+        return {"unavailable": "oracle/_ref/kernels_cuda not built (needs /root/reference at build time)"}
+    dev = sc["pos"].device
+    tet = torch.from_numpy(grid.tets).to(dev)
+    inv = orc_e.tet_inverse_v(torch.from_numpy(grid.centred()), torch.from_numpy(grid.tets)).to(dev)
+    faces_i, counts, _ = surface.boundary_faces(eng.face_table, sc["occ"], Fmax)
+    counts_h = counts.tolist()
+    gen = torch.Generator(device=dev).manual_seed(3)
+    parts = {}
+
+    def timed(name, fn, reps=1):
+        fn()                                   # warm-up (module load, allocator)
+        parts[name] = parts.get(name, 0.0) + ref_cuda.time_ms(fn, reps)
+
+    timed("energies_torch_fwd_bwd", lambda: orc_e.energies_with_grad(sc["pos"], tet, inv, (1.0, 1.0, 1e6)), reps=3)
+    soup = orc_e.gather_tets(sc["pos"], tet).contiguous()
+    timed("A1_point_in_tet", lambda: ref_cuda.point_in_tet(soup, sc["pts"]))
+    del soup
+    for b in range(B):                         # the reference's per-sample surface loop
+        nb = int(counts_h[b])
+        if nb == 0:
+            continue
+        f = faces_i[b, :nb].long()
+        face_pos = sc["pos"][b][f.reshape(-1)].reshape(1, nb, 3, 3).contiguous()
+        u = torch.sqrt(torch.rand(1, nb, S_face, 1, device=dev, generator=gen))
+        v = torch.rand(1, nb, S_face, 1, device=dev, generator=gen)
+        pred = ((1 - u) * face_pos[:, :, 0:1] + u * (1 - v) * face_pos[:, :, 1:2] + u * v * face_pos[:, :, 2:3]).reshape(1, -1, 3).contiguous()
+        gt = sc["gt"][b:b + 1].contiguous()
+        timed("A2_nearest_neighbor", lambda: ref_cuda.nearest_neighbor(pred, gt))
+        res = {}
+
+        def fwd():
+            res["d"], res["f"] = ref_cuda.point_face_distance(gt, face_pos)
+        timed("A4_distance_fwd", fwd)
+        gd = torch.ones_like(res["d"])
+        timed("A4_distance_bwd", lambda: ref_cuda.point_face_distance_bwd(gt, face_pos, res["f"], gd))
+        timed("A5_face_adjacency", lambda: ref_cuda.face_adjacency(face_pos[0]))
+    total = float(sum(parts.values()))
+    return {"value": B * T / total, "unit": "tets/ms", "ms_per_step": total, "parts_ms": {k: round(v, 3) for k, v in parts.items()},
+            "kind": "reference CUDA kernels (unmodified __global__ code of the reference's extensions, sm_100a build) + reference "
+                    "pure-PyTorch energies on the GPU; glue (sampling, sqrt/mean reductions, A3 gathers) not counted",
+            "boundary_faces_per_sample": [int(c) for c in counts_h]}
+
+
 # ------------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -198,6 +251,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--serial", action="store_true", help="enqueue the loss groups on one stream (profiling)")
+    ap.add_argument("--skip-ref-cuda", action="store_true", help="do not time the reference's own CUDA kernels beside ours")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -364,12 +418,19 @@ def main():
                 cpu = {"value": v, "unit": "tets/ms", "cores": cores, "kind": "port", "sample": desc}
             except Exception as e:  # pragma: no cover
                 cpu = {"value": None, "unit": "tets/ms", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %s" % str(e)[:120]}
+        ref_cuda_leg = None
+        if not args.skip_ref_cuda and world == 1:
+            try:
+                ref_cuda_leg = reference_cuda_step(eng, grid, scenes[0], Fmax, S_face, B, T)
+            except Exception as e:  # pragma: no cover
+                ref_cuda_leg = {"unavailable": "failed: %s" % str(e)[:160]}
         config["graph"] = config.get("graph", "cuda graph replay" if graphs is not None else "eager")
         line = {"metric": "tets/ms fwd+bwd (occ+AMIPS+chamfer) res-%d" % args.res, "value": value, "unit": "tets/ms", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "tets/ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "loss": float(l.item())}
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "reference_cuda": ref_cuda_leg,
+                "loss": float(l.item())}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

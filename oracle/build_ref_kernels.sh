@@ -30,3 +30,21 @@ build face_distance_bwd "$TMP/a4b_body.cuh" "$HERE/ref_kernels_driver_a4b.inc"
 cut_body "$REF/layers/DefTet/tet_face_adj_m_idx/tet_face_adj_m_for.cu" '^void dr_cuda_forward_batch' "$TMP/a5_body.cuh"
 build face_adj "$TMP/a5_body.cuh" "$HERE/ref_kernels_driver_a5.inc"
 echo "build_ref_kernels: built $(ls "$OUT" | tr '\n' ' ')"
+
+# ---- the same reference kernels compiled FOR THE DEVICE (sm_100a): the reference's own __global__ kernels, unmodified, behind
+# small extern "C" launchers (oracle/ref_kernels_cuda_driver_*.inc, ours) that take raw device pointers instead of at::Tensor.
+# This is the "reference's own CUDA extensions" arm of the measurement: default nvcc code generation
+# (FMA contraction on, like the reference's torch cpp_extension build), the reference's launch geometry.  Runs only on the GPU box.
+OUTD="$HERE/_ref/kernels_cuda"
+mkdir -p "$OUTD"
+build_dev() {  # $1 = name, $2 = body file, $3 = driver
+    { echo '#include <cuda_runtime.h>'; echo '#include <math.h>'; echo '#include <stdint.h>'; echo '#include <stdio.h>'; cat "$2"; cat "$3"; } > "$TMP/$1_dev.cu"
+    nvcc -O3 -w -std=c++14 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -shared -o "$OUTD/$1.so" "$TMP/$1_dev.cu" -lcudart
+}
+build_dev point_in_tet "$TMP/a1_body.cuh" "$HERE/ref_kernels_cuda_driver_a1.inc"
+build_dev face_distance_fwd "$TMP/a4f_body.cuh" "$HERE/ref_kernels_cuda_driver_a4f.inc"
+build_dev face_distance_bwd "$TMP/a4b_body.cuh" "$HERE/ref_kernels_cuda_driver_a4b.inc"
+build_dev face_adj "$TMP/a5_body.cuh" "$HERE/ref_kernels_cuda_driver_a5.inc"
+grep -v '#include <ATen' "$REF/layers/nearest_neighbor/nearest_neighbor_cuda.cu" > "$TMP/a2_body.cuh"
+build_dev nearest_neighbor "$TMP/a2_body.cuh" "$HERE/ref_kernels_cuda_driver_a2.inc"
+echo "build_ref_kernels: built (device) $(ls "$OUTD" | tr '\n' ' ')"

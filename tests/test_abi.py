@@ -64,3 +64,16 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, os.path.join(dirpath, f)
+
+
+def test_reference_device_kernels_are_built_and_export_their_launchers():
+    """oracle/_ref/kernels_cuda (the reference's own __global__ kernels compiled for sm_100a; test / bench baseline only)."""
+    names = {"point_in_tet": "refcuda_point_in_tet", "nearest_neighbor": "refcuda_nearest_neighbor",
+             "face_distance_fwd": "refcuda_point_face_distance", "face_distance_bwd": "refcuda_point_face_distance_bwd",
+             "face_adj": "refcuda_face_adjacency"}
+    d = os.path.join(ROOT, "oracle", "_ref", "kernels_cuda")
+    if not os.path.isdir(d):
+        pytest.skip("oracle/_ref/kernels_cuda not built (needs /root/reference at build time)")
+    for name, sym in names.items():
+        lib = ctypes.CDLL(os.path.join(d, name + ".so"))
+        assert hasattr(lib, sym), (name, sym)
