@@ -132,3 +132,56 @@ def test_c_restatement_matches_reference_device_functions_compiled_for_host():
     assert np.array_equal(f, fr) and np.array_equal(d, dr)
     gd = torch.rand(1, 500, 1, generator=gen).numpy()
     assert np.array_equal(native.point_face_distance_bwd(q, rs, f, gd), native.ref_point_face_distance_bwd(q, rs, fr, gd))
+
+
+# ---- diff_render topology / regulariser oracle vs the reference's own Python (tests/golden/make_golden_diffrender.py) ----------
+def _dr():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "diffrender_res8.npz"))
+
+
+def test_topology_oracle_edges_and_subdivision_match_reference():
+    from oracle import topology as orc_t
+    G = _dr()
+    edges, te = orc_t.tet_edges(G["tets"])
+    assert np.array_equal(edges, G["edges"]) and np.array_equal(te, G["tet_edge"])
+    for name, sig in (("sub_all", None), ("sub_sig", G["sub_sig"])):
+        p, f, t = orc_t.subdivide(G["tets"], G["points"], G["feat"], sig)
+        assert np.array_equal(p, G[name + "_points"]) and np.array_equal(f, G[name + "_feat"])      # midpoints: bit-identical
+        assert np.array_equal(t, G[name + "_tets"])
+
+
+def test_topology_oracle_geometry_tables_match_reference():
+    from oracle import topology as orc_t
+    G = _dr()
+    P = G["points"].shape[0]
+    f3, ft2, fs2 = orc_t.tet_to_face_idx(P, G["tets"])
+    assert np.array_equal(f3, G["face_fx3"]) and np.array_equal(ft2, G["face_tet_fx2"]) and np.array_equal(fs2, G["face_slot_fx2"])
+    nbr = orc_t.tet_neighbours(G["tets"], P)
+    assert np.array_equal(np.sort(nbr, axis=1), np.sort(G["tet_neighbour_idx"], axis=1))        # same neighbour sets (slot order differs)
+    table, deg = orc_t.point_adj_idx(P, G["tets"])
+    assert np.array_equal(table, G["point_adj_idx"]) and np.array_equal(deg, G["point_adj_sum"])
+    for L in (1, 2, 3):
+        for thres in (0.05, 0.5):
+            kept, _ = orc_t.delete_tets(G["tets"], G["point_weights"], nbr, L, thres)
+            assert np.array_equal(kept, G["del_L%d_t%03d" % (L, int(thres * 100))])
+
+
+def test_topology_oracle_regularisers_and_projection_match_reference():
+    import torch
+    from oracle import topology as orc_t
+    G = _dr()
+    x = torch.from_numpy(G["feat"][:, :4]).clone().requires_grad_(True)
+    lap = orc_t.featlap(x, torch.from_numpy(G["point_adj_idx"]), torch.from_numpy(G["point_adj_sum"]) + 1e-10)
+    (lap * torch.from_numpy(G["featlap_gout"])).sum().backward()
+    assert np.allclose(lap.detach().numpy(), G["featlap"], rtol=1e-6, atol=1e-7) and np.allclose(x.grad.numpy(), G["featlap_gx"], rtol=1e-5, atol=1e-7)
+    p = torch.from_numpy(G["points"]).clone().requires_grad_(True)
+    vv = orc_t.volume_deviation(p, torch.from_numpy(G["tets"]))
+    (vv * torch.from_numpy(G["volvar_gout"])).sum().backward()
+    assert rel_err(vv.detach(), G["volvar"]) < 1e-5 and rel_err(p.grad, G["volvar_gpoint"]) < 1e-5       # V - mean(V) cancels: max-normalised
+    pts = torch.from_numpy(G["points"]).unsqueeze(0).repeat(2, 1, 1)
+    cam, img = orc_t.perspective(pts, torch.from_numpy(G["cam_rot"]), torch.from_numpy(G["cam_pos"]), torch.from_numpy(G["cam_proj"]))
+    assert np.array_equal(cam.numpy(), G["points_camera"]) and np.array_equal(img.numpy(), G["points_image"])
+    f3 = torch.from_numpy(G["face_fx3"])
+    assert np.array_equal(orc_t.vertex2face(cam, f3).numpy(), G["face_cam_bxfx9"])
+    col, vis = orc_t.peel2mask(torch.from_numpy(G["peel_in"]))
+    assert np.allclose(col.numpy(), G["peel_color"], rtol=1e-6, atol=1e-7) and np.allclose(vis.numpy(), G["peel_vis"], rtol=1e-6, atol=1e-7)
