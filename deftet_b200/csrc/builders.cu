@@ -255,6 +255,43 @@ __global__ void __launch_bounds__(256) collapse_emit_kernel(const int32_t* __res
     if (is_first[i]) inverse_idx[uid[i]] = i;
 }
 
+// ---- N3: face table with boundary faces in one first-occurrence order, and the tet neighbour table ---------------
+//   3_model/prepare_for_wz.py:49-108 tet_to_face_idx(with_boundary=True);  3_model/utils_tetsv.py:16-62 tet_neighbour_idx
+__global__ void __launch_bounds__(256) face_mark_all_kernel(const unsigned* __restrict__ run_len, const unsigned* __restrict__ sorted_slot,
+                                                            size_t n, unsigned* __restrict__ flag, unsigned* __restrict__ partner) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    unsigned len = run_len[p];
+    if (len == 1 || len == 2) {
+        unsigned s0 = sorted_slot[p];
+        flag[s0] = 1u;
+        partner[s0] = len == 2 ? sorted_slot[p + 1] : 0xffffffffu;
+    }
+}
+__global__ void __launch_bounds__(256) face_emit_all_kernel(const int32_t* __restrict__ tet, size_t n, const unsigned* __restrict__ flag,
+                                                            const unsigned* __restrict__ pos, const unsigned* __restrict__ partner,
+                                                            int32_t* __restrict__ face_fx3, int32_t* __restrict__ face_tet_fx2,
+                                                            int32_t* __restrict__ face_slot_fx2) {
+    size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n || !flag[s]) return;
+    unsigned o = pos[s], s1 = partner[s];
+    int a, b, c;
+    tet_face_verts(tet, (int)s, a, b, c);
+    face_fx3[(size_t)o * 3] = a; face_fx3[(size_t)o * 3 + 1] = b; face_fx3[(size_t)o * 3 + 2] = c;
+    bool two = s1 != 0xffffffffu;
+    if (face_tet_fx2) { face_tet_fx2[(size_t)o * 2] = (int)(s >> 2); face_tet_fx2[(size_t)o * 2 + 1] = two ? (int)(s1 >> 2) : -1; }
+    if (face_slot_fx2) { face_slot_fx2[(size_t)o * 2] = (int)(s & 3); face_slot_fx2[(size_t)o * 2 + 1] = two ? (int)(s1 & 3) : -1; }
+}
+// nbr[4t+i] = the tet across local face i of tet t, -1 on the boundary (pre-filled by the caller)
+__global__ void __launch_bounds__(256) neighbour_kernel(const unsigned* __restrict__ run_len, const unsigned* __restrict__ sorted_slot, size_t n,
+                                                        int32_t* __restrict__ nbr) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n || run_len[p] != 2) return;
+    unsigned s0 = sorted_slot[p], s1 = sorted_slot[p + 1];
+    nbr[s0] = (int)(s1 >> 2);
+    nbr[s1] = (int)(s0 >> 2);
+}
+
 static int key_bits_for(u64 max_key) { int b = 1; while (b < 64 && (max_key >> b)) ++b; return b; }
 
 }  // namespace dtb
@@ -326,6 +363,55 @@ extern "C" int dtb_tet_to_face(const int32_t* tet, int n_point, int T, int32_t* 
     face_emit_kernel<<<blocks, 256, 0, st>>>(tet, n, pair_flag, pair_pos, partner, single_flag, single_pos, face_fx3, face_tet_fx2,
                                              face_slot_fx2, boundary_fx3);
     DTB_LAUNCH_CHECK("face_emit");
+    return DTB_OK;
+}
+
+extern "C" size_t dtb_tet_to_face_idx_workspace(int T) {
+    size_t n = (size_t)T * 4;
+    return face_sort_ws(n) + 3 * align_up(n * 4, 256) + scan_workspace_bytes(n) + 1024;
+}
+// Interior AND boundary faces in one list, in first-occurrence order; boundary faces carry -1 in the second column of
+// face_tet_fx2 / face_slot_fx2.  *n_face = number of rows written (capacity needed: 4T rows).
+extern "C" int dtb_tet_to_face_idx(const int32_t* tet, int n_point, int T, int32_t* face_fx3, int32_t* face_tet_fx2, int32_t* face_slot_fx2,
+                                   int32_t* n_face, void* workspace, size_t workspace_bytes, void* stream) {
+    DTB_REQUIRE(tet && face_fx3 && n_face, "tet_to_face_idx: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (T == 0) { DTB_CUDA(cudaMemsetAsync(n_face, 0, sizeof(int32_t), st)); return DTB_OK; }
+    if (!workspace) { set_error("tet_to_face_idx: null workspace"); return DTB_EWORKSPACE; }
+    Workspace ws(workspace, workspace_bytes);
+    FaceSort fs;
+    int rc = face_sort(tet, n_point, T, ws, fs, st);
+    if (rc) return rc;
+    size_t n = fs.n;
+    unsigned* flag = ws.take<unsigned>(n); unsigned* partner = ws.take<unsigned>(n); unsigned* pos = ws.take<unsigned>(n);
+    size_t sb = scan_workspace_bytes(n);
+    void* sws = ws.take<char>(sb);
+    if (!ws.ok || !workspace) { set_error("tet_to_face_idx: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return DTB_EWORKSPACE; }
+    DTB_CUDA(cudaMemsetAsync(flag, 0, n * 4, st));
+    int blocks = cdiv((long long)n, 256);
+    face_mark_all_kernel<<<blocks, 256, 0, st>>>(fs.run_len, fs.slot, n, flag, partner);
+    DTB_LAUNCH_CHECK("face_mark_all");
+    rc = exclusive_scan_u32(flag, pos, n, (unsigned*)n_face, sws, sb, st);
+    if (rc) return rc;
+    face_emit_all_kernel<<<blocks, 256, 0, st>>>(tet, n, flag, pos, partner, face_fx3, face_tet_fx2, face_slot_fx2);
+    DTB_LAUNCH_CHECK("face_emit_all");
+    return DTB_OK;
+}
+
+extern "C" size_t dtb_tet_neighbours_workspace(int T) { return face_sort_ws((size_t)T * 4) + 1024; }
+extern "C" int dtb_tet_neighbours(const int32_t* tet, int n_point, int T, int32_t* neighbour_tx4, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+    DTB_REQUIRE(T == 0 || (tet && neighbour_tx4), "tet_neighbours: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (T == 0) return DTB_OK;
+    if (!workspace) { set_error("tet_neighbours: null workspace"); return DTB_EWORKSPACE; }
+    Workspace ws(workspace, workspace_bytes);
+    FaceSort fs;
+    int rc = face_sort(tet, n_point, T, ws, fs, st);
+    if (rc) return rc;
+    DTB_CUDA(cudaMemsetAsync(neighbour_tx4, 0xff, fs.n * 4, st));
+    neighbour_kernel<<<cdiv((long long)fs.n, 256), 256, 0, st>>>(fs.run_len, fs.slot, fs.n, neighbour_tx4);
+    DTB_LAUNCH_CHECK("neighbour");
     return DTB_OK;
 }
 

@@ -278,6 +278,70 @@ int dtb_laplacian_forward(const float* d, const int32_t* edges, const float* wei
 int dtb_laplacian_backward(const float* resid_ws, const int32_t* edges, const float* weight, const unsigned* rows_ws,
                            const float* g_loss, int B, int V, float* grad, void* stream);
 
+/* ---- N3: topology editing + regularisers of the diff_render optimisation loop ---------
+ * The reference runs these on the host in numpy / Python loops (diff_render/diftet_6_subdiv/3_model); every
+ * index-valued output below is in the reference's order.
+ *
+ * dtb_tet_edges: unique undirected edges (lo,hi) sorted lexicographically -> edges (<=6T,2) i32, *n_edge; tet_edge (T,6)
+ *   i32 = edge id of the vertex pairs (0,1),(0,2),(0,3),(1,2),(1,3),(2,3) of each tet (may be NULL).
+ *   prepare_for_wz.py:186-205 generate_edge, :208-238 matchedgelist / generate_tet_edge_idx.
+ * dtb_subdivide_tets: 1->8 split of the tets flagged in subdiv (u8 per tet; NULL = all): out_tet gets the unflagged tets in
+ *   order, then 8 children per flagged tet; new vertex id of edge e is n_point + e.  Capacity 8T rows; *n_out = rows.
+ *   prepare_for_wz.py:257-301 generate_subdivision.
+ * dtb_edge_midpoints: out (E,K) = (values[e0] + values[e1]) / 2 (positions, features, pointmov alike); :241-254.
+ * dtb_tet_to_face_idx: unique faces, interior and boundary, first-occurrence order, -1 partner on the boundary.
+ *   prepare_for_wz.py:49-108 tet_to_face_idx(with_boundary=True) as 3_model/deftet.py:141-143 calls it.
+ * dtb_tet_neighbours: (T,4) i32, column i = tet across local face i ((0,1,2),(1,0,3),(2,3,0),(3,2,1)), -1 = none.
+ *   utils_tetsv.py:16-62 tet_adj_share -> tet_neighbour_idx (same neighbour sets; the reference's column order is Python
+ *   dict order, its consumers only take row maxima).
+ * dtb_point_adj_rows / dtb_point_adj_table: fixed-width vertex neighbour table from the sorted directed edge list of
+ *   dtb_tet_point_adj: rows() gives row_start/row_end (P,) i32, degree (P,) f32 and *max_degree; table() fills (P,M) i32,
+ *   ascending neighbour ids, -1 padding.  prepare_for_wz.py:112-137 generate_point_adj(_idx).
+ * dtb_tet_delete: keep tet t iff max over the vertex weights of all tets reached by `levels`-step walks through the neighbour
+ *   table exceeds thres (a walk that leaves the mesh contributes 0); compacts the kept tets, *n_out = count, keep (T,) u8
+ *   optional.  3_model/deftet.py:290-329 pointweights2tetweights / tetweights2tetneighbourweights / deletetet and
+ *   prepare_for_wz.py:171-181 delete_tet (the reference materialises a (T, 4^(levels+1)) table).
+ * dtb_featlap_*: out (P,C) = (sum_{j in table[i]} x_j / weight_i - x_i)^2; backward ACCUMULATES into grad_x (P,C).
+ *   3_model/deftet.py:227-250 get_featlap (+ autograd).
+ * dtb_tet_volume_deviation_*: out (T,) = V_t - mean V, V = signed volume of scale*pos; acc = one f64 of scratch; backward
+ *   ACCUMULATES into grad_pos (P,3).  3_model/deftet.py:252-309 get_volume_variance (+ autograd).
+ * dtb_project_faces_*: camera transform, perspective divide, optional sigmoid and per-face gather in one pass:
+ *   face_z (B,F,3) camera-space z, face_xy (B,F,3,2) image xy * multiplier, face_feat (B,F,3,D); pos (P,3) and feat (P,D) are
+ *   shared by the B views, cam_rot (B,3,3), cam_pos (B,3), cam_proj (3,).  backward ACCUMULATES into grad_pos (P,3) and
+ *   grad_feat (P,D); any of g_face_* / grad_* may be NULL.  3_model/cameraop.py:14-33 perspective, 4_render/vertex2face.py:14-28,
+ *   5_rendereq/deftetrneder.py:84 (sigmoid), 3_model/deftet.py:425-470 (the repeat over views). */
+size_t dtb_tet_edges_workspace(int T);
+int dtb_tet_edges(const int32_t* tet, int n_point, int T, int32_t* edges, int32_t* tet_edge, int32_t* n_edge, void* workspace,
+                  size_t workspace_bytes, void* stream);
+size_t dtb_subdivide_tets_workspace(int T);
+int dtb_subdivide_tets(const int32_t* tet, const int32_t* tet_edge, const unsigned char* subdiv, int n_point, int T,
+                       int32_t* out_tet, int32_t* n_out, void* workspace, size_t workspace_bytes, void* stream);
+int dtb_edge_midpoints(const float* values, int K, const int32_t* edges, int E, float* out, void* stream);
+size_t dtb_tet_to_face_idx_workspace(int T);
+int dtb_tet_to_face_idx(const int32_t* tet, int n_point, int T, int32_t* face_fx3, int32_t* face_tet_fx2, int32_t* face_slot_fx2,
+                        int32_t* n_face, void* workspace, size_t workspace_bytes, void* stream);
+size_t dtb_tet_neighbours_workspace(int T);
+int dtb_tet_neighbours(const int32_t* tet, int n_point, int T, int32_t* neighbour_tx4, void* workspace, size_t workspace_bytes,
+                       void* stream);
+int dtb_point_adj_rows(const int32_t* edges, int E, int n_point, int32_t* row_start, int32_t* row_end, float* degree,
+                       int32_t* max_degree, void* stream);
+int dtb_point_adj_table(const int32_t* edges, int E, int n_point, const int32_t* row_start, int M, int32_t* table, void* stream);
+size_t dtb_tet_delete_workspace(int T);
+int dtb_tet_delete(const int32_t* tet, const float* point_weight, const int32_t* neighbour, int T, int levels, float thres,
+                   int32_t* out_tet, int32_t* n_out, unsigned char* keep, void* workspace, size_t workspace_bytes, void* stream);
+int dtb_featlap_forward(const float* x, const int32_t* table, const float* weight, int P, int M, int C, float* out, void* stream);
+int dtb_featlap_backward(const float* x, const int32_t* table, const float* weight, const float* g_out, int P, int M, int C,
+                         float* grad_x, void* stream);
+int dtb_tet_volume_deviation_forward(const float* pos, const int32_t* tet, int T, float scale, float* out, double* acc, void* stream);
+int dtb_tet_volume_deviation_backward(const float* pos, const int32_t* tet, int T, float scale, const float* g_out, double* acc,
+                                      float* grad_pos, void* stream);
+int dtb_project_faces_forward(const float* pos, const float* feat, const int32_t* faces, const float* cam_rot, const float* cam_pos,
+                              const float* cam_proj, int B, int F, int D, float multiplier, int sigmoid, float* face_z,
+                              float* face_xy, float* face_feat, void* stream);
+int dtb_project_faces_backward(const float* pos, const float* feat, const int32_t* faces, const float* cam_rot, const float* cam_pos,
+                               const float* cam_proj, int B, int F, int D, float multiplier, int sigmoid, const float* g_face_xy,
+                               const float* g_face_feat, const float* g_face_z, float* grad_pos, float* grad_feat, void* stream);
+
 /* ---- device-wide primitives (exported for the self-tests; also usable by integrators) ----------------- */
 size_t dtb_prim_scan_workspace(size_t n);
 int dtb_prim_exclusive_scan_u32(const unsigned* in, unsigned* out, size_t n, unsigned* total, void* ws, size_t ws_bytes,
