@@ -27,11 +27,19 @@ def emit(**kw):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="", help="comma list of sections: core (A1-A16 rows), n3 (topology/regulariser kernels), diffrender (config-5 step)")
     a = ap.parse_args()
+    only = set(x for x in a.only.split(",") if x)
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     from oracle import native
+    if not only or "n3" in only:
+        section_n3(dev, flush, peak, a.quick)
+    if not only or "diffrender" in only:
+        section_diffrender(dev, flush, a.quick)
+    if only and "core" not in only:
+        return
 
     # ---- config 2: res 40, batch 8, energies fwd+bwd (A6-A8) ------------------------------------------------------
     for res, B in ((40, 8), (70, 8), (100, 4)):
@@ -146,6 +154,116 @@ def main():
     cen = pos[:1, tet.long().reshape(-1)].reshape(1, -1, 4, 3).mean(2).contiguous()
     med, _ = timeit(lambda: render.check_sign(verts, torch.from_numpy(f).to(dev), cen), 5, 2, flush)
     emit(row="A16 check_sign", mesh_faces=int(f.shape[0]), points=int(cen.shape[1]), ms=med, tets_per_ms=cen.shape[1] / med)
+
+
+def section_n3(dev, flush, peak, quick):
+    """N3 rows: topology editing + regularisers + fused projection at the shipped-grid scales (res 40 / 60)."""
+    from deftet_b200 import topology
+    for res in ((40,) if quick else (40, 60)):
+        g = acute_lattice_grid(res)
+        V, T = g.n_vert, g.n_tet
+        tet = torch.from_numpy(g.tets).to(dev).to(torch.int32)
+        pts = torch.from_numpy(g.centred()).to(dev)
+        feat = torch.rand(V, 7, device=dev)
+        med, _ = timeit(lambda: topology.tet_edges(tet, V), 5, 2, flush)
+        emit(row="N3 tet_edges (generate_edge + generate_tet_edge_idx)", res=res, V=V, T=T, ms=med, tets_per_ms=T / med)
+        med, _ = timeit(lambda: topology.generate_subdivision(tet, pts, feat, None), 5, 2, flush)
+        p2, f2, t2 = topology.generate_subdivision(tet, pts, feat, None)
+        emit(row="N3 generate_subdivision (all tets 1->8)", res=res, V=V, T=T, V_out=int(p2.shape[0]), T_out=int(t2.shape[0]), ms=med, tets_per_ms=T / med)
+
+        def geometry():
+            topology.tet_to_face_idx(V, tet, True); topology.tet_neighbours(tet, V); topology.generate_point_adj_idx(V, tet)
+        med, _ = timeit(geometry, 5, 2, flush)
+        emit(row="N3 updategeometry (tet_to_face_idx + tet_neighbours + point_adj_idx)", res=res, V=V, T=T, ms=med, tets_per_ms=T / med)
+        nbr = topology.tet_neighbours(tet, V)
+        w = torch.rand(V, 1, device=dev) ** 4
+        med, _ = timeit(lambda: topology.delete_tet_by_weight(tet, w, nbr, 0.3, 3), 5, 2, flush)
+        emit(row="N3 deletetet (3 neighbour levels)", res=res, V=V, T=T, ms=med, tets_per_ms=T / med)
+        table, adjsum = topology.generate_point_adj_idx(V, tet)
+        x = feat.clone().requires_grad_(True)
+
+        def lap():
+            x.grad = None
+            topology.featlap(x, table, adjsum + 1e-10).sum().backward()
+        med, _ = timeit(lap, 10, 3, flush)
+        by = 2 * (V * table.shape[1] * 4 + 3 * V * 7 * 4)
+        emit(row="N3 get_featlap fwd+bwd (7 channels)", res=res, V=V, M=int(table.shape[1]), ms=med, algorithmic_bytes=by, hbm_frac=by / (med * 1e-3) / 1e9 / peak)
+        pp = pts.clone().requires_grad_(True)
+
+        def vol():
+            pp.grad = None
+            (topology.volume_deviation(pp, tet) ** 2).sum().backward()
+        med, _ = timeit(vol, 10, 3, flush)
+        by = 2 * (16 * T + 12 * V) + 8 * T + 12 * V
+        emit(row="N3 get_volume_variance fwd+bwd", res=res, V=V, T=T, ms=med, tets_per_ms=T / med, algorithmic_bytes=by, hbm_frac=by / (med * 1e-3) / 1e9 / peak)
+        faces = topology.tet_to_face_idx(V, tet, True)[0]
+        F = faces.shape[0]
+        rot = torch.eye(3, device=dev).unsqueeze(0)
+        cpos = torch.tensor([[0.0, 0.0, 4.0]], device=dev)
+        proj = torch.tensor([2.0, 2.0, -1.0], device=dev)
+        ff4 = torch.rand(V, 4, device=dev, requires_grad=True)
+
+        def prj():
+            pp.grad = None; ff4.grad = None
+            fz, fxy, ff = topology.project_faces(pp, ff4, faces, rot, cpos, proj, 1000.0, True)
+            (fxy.sum() + ff.sum()).backward()
+        med, _ = timeit(prj, 10, 3, flush)
+        by = 2 * (12 * F + F * 3 * (4 + 8 + 16)) + 28 * V * 2
+        emit(row="N3 project_faces fwd+bwd (1 view, 4 features)", res=res, V=V, faces=int(F), ms=med, algorithmic_bytes=by, hbm_frac=by / (med * 1e-3) / 1e9 / peak)
+
+
+def section_diffrender(dev, flush, quick):
+    """Config 5 (BASELINE.json configs[4]): one optimisation step of the diff_render loop through the Deftet model mirror -- res-40
+    grid x tetcoef 2.5, one 800x800 view, ALL pixels, K=300, L1 image + mask loss, occupancy / Laplacian / volume regularisers,
+    backward, Adam step (6_optim/optim_with_mask_subdiv_from_gridmov.py:186-283)."""
+    import tempfile
+    from deftet_b200 import diffrender
+    W = 400 if quick else 800
+    K = 300
+    with tempfile.TemporaryDirectory() as d:
+        model = diffrender.Deftet(d, res=40, coef=2.5, feature_dim=4, seed=0, device=dev)
+    model.sethw(W, W, 1000)
+    focal = 0.5 * W / np.tan(0.5 * 0.6911)
+    proj = torch.tensor([focal / (0.5 * W), focal / (0.5 * W), -1.0], device=dev).reshape(3, 1)
+    n_view = 8
+    th = np.linspace(0, 2 * np.pi, n_view, endpoint=False)
+    rots = torch.from_numpy(np.stack([np.array([[np.cos(t), 0, np.sin(t)], [0, 1, 0], [-np.sin(t), 0, np.cos(t)]]) for t in th]).astype(np.float32)).to(dev)
+    poss = torch.stack([rots[b].t() @ torch.tensor([0.0, 0.0, 4.0], device=dev) for b in range(n_view)])
+    sample = torch.ones(W, W, dtype=torch.bool, device=dev)
+    gt_im = torch.rand(1, W * W, 3, device=dev)
+    gt_mask = (torch.rand(1, W * W, 1, device=dev) > 0.5).float()
+    opt_g = torch.optim.Adam(list(model.parameters())[1:], lr=1e-2)
+    opt_d = torch.optim.Adam(list(model.parameters())[:1], lr=1e-4)
+    wvec = torch.tensor([1.0, 1.0, 1.0, 1.0, 10.0, 10.0, 10.0], device=dev)
+    state = {"k": 0}
+
+    def step():
+        k = state["k"] % n_view
+        state["k"] += 1
+        opt_g.zero_grad(set_to_none=True); opt_d.zero_grad(set_to_none=True)
+        col, mask = model(sample, rots[k:k + 1], poss[k:k + 1], proj, diffrender.rendermeshcolor, knum=K)
+        loss = torch.nn.functional.l1_loss(col, gt_im) + torch.nn.functional.l1_loss(mask, gt_mask)
+        w, c = diffrender.preprocess_save(None, model.get_feat())
+        mov = model.get_mov()
+        loss = loss + 1e-3 * w.mean() + 1e-2 * mov.abs().mean() + 1e2 * (model.get_volume_variance() ** 2).sum()
+        lap = model.get_featlap(torch.cat([c, w, mov], dim=-1)).sum(0)
+        loss = loss + torch.dot(lap, wvec) * 1e-4
+        loss.backward()
+        opt_g.step(); opt_d.step()
+    med, mn = timeit(step, 8, 3, flush)
+    F, T, V = int(model.tff_fx3.shape[0]), int(model.tftet_tx4.shape[0]), int(model.n_point)
+    emit(row="config 5: diff_render optimisation step (fused projection + rasterizer + compositor, regularisers, Adam)", pixels=W * W, faces=F, T=T,
+         V=V, K=K, ms=med, ms_min=mn, views_per_s=1e3 / med, tets_per_ms=T / med)
+    with torch.no_grad():
+        med, _ = timeit(lambda: model(sample, rots[:1], poss[:1], proj, diffrender.rendermeshcolor, knum=K), 5, 2, flush)
+    emit(row="config 5: diff_render forward only (one 800x800 view)" if W == 800 else "config 5 (quick): forward only", pixels=W * W, faces=F, K=K, ms=med)
+    # topology edit of the same model: 1->8 subdivision incl. rebuilding every table (Deftet.subdivision)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    model.subdivision(None)
+    torch.cuda.synchronize()
+    emit(row="config 5: Deftet.subdivision(None) incl. updategeometry (wall clock)", T_in=T, T_out=int(model.tftet_tx4.shape[0]), V_out=int(model.n_point),
+         ms=(time.perf_counter() - t0) * 1e3)
 
 
 if __name__ == "__main__":
