@@ -342,6 +342,15 @@ int dtb_project_faces_backward(const float* pos, const float* feat, const int32_
                                const float* cam_proj, int B, int F, int D, float multiplier, int sigmoid, const float* g_face_xy,
                                const float* g_face_feat, const float* g_face_z, float* grad_pos, float* grad_feat, void* stream);
 
+/* ---- N4: evaluation metric next to the hot path ---------------------------------------
+ * Exact squared distance from each point to the closest triangle of a mesh; stand-in for
+ * kal.metrics.trianglemesh.point_to_mesh_distance at utils/point_cloud_utils.py:48-56 (hausdorff_distance) -- Kaolin is
+ * un-vendored and un-pinned: parity unpinned, contract in oracle/metrics.py.  points (B,P,3), face_vertices (B,F,3,3);
+ * dist (B,P) f32, face_idx (B,P) i64 (first strict minimum in face order; may be NULL), dist_type (B,P) i32 (0 interior,
+ * 1-3 vertex, 4-6 edge ab/bc/ca; may be NULL).  Forward only (the reference uses it under no_grad in evaluation). */
+int dtb_point_to_mesh_distance(const float* points, const float* face_vertices, int B, int P, int F, float* dist,
+                               long long* face_idx, int32_t* dist_type, void* stream);
+
 /* ---- device-wide primitives (exported for the self-tests; also usable by integrators) ----------------- */
 size_t dtb_prim_scan_workspace(size_t n);
 int dtb_prim_exclusive_scan_u32(const unsigned* in, unsigned* out, size_t n, unsigned* total, void* ws, size_t ws_bytes,

@@ -185,3 +185,24 @@ def test_topology_oracle_regularisers_and_projection_match_reference():
     assert np.array_equal(orc_t.vertex2face(cam, f3).numpy(), G["face_cam_bxfx9"])
     col, vis = orc_t.peel2mask(torch.from_numpy(G["peel_in"]))
     assert np.allclose(col.numpy(), G["peel_color"], rtol=1e-6, atol=1e-7) and np.allclose(vis.numpy(), G["peel_vis"], rtol=1e-6, atol=1e-7)
+
+
+def test_metrics_oracle_point_triangle_distance_is_a_true_minimum():
+    """oracle/metrics.py (parity unpinned: Kaolin absent) -- self-check of the restated contract: the closed-form distance is a lower
+    bound of, and converges to, the distance to densely sampled points of the triangle."""
+    from oracle import metrics as orc_m
+    rng = np.random.RandomState(0)
+    fv = rng.rand(1, 40, 3, 3) - 0.5
+    fv[0, :5, 2] = fv[0, :5, 1] + 1e-9 * rng.rand(5, 3)            # needle triangles
+    pts = (rng.rand(1, 60, 3) - 0.5) * 2
+    d, f = orc_m.point_to_mesh_distance(pts, fv)
+    n = 60
+    u, v = np.meshgrid(np.linspace(0, 1, n), np.linspace(0, 1, n), indexing="ij")
+    keep = (u + v) <= 1.0
+    u, v = u[keep], v[keep]
+    samples = (fv[0, :, None, 0] * (1 - u - v)[None, :, None] + fv[0, :, None, 1] * u[None, :, None] + fv[0, :, None, 2] * v[None, :, None])   # (F,S,3)
+    ds = ((pts[0][:, None, None, :] - samples[None]) ** 2).sum(-1).min(-1)                                                           # (P,F)
+    assert np.all(d[0] <= ds.min(-1) + 1e-12)
+    assert np.allclose(np.sqrt(d[0]), np.sqrt(ds.min(-1)), atol=2.0 / n)
+    sd, si = orc_m.sided_distance(pts, fv[:, :, 0])
+    assert sd.shape == (1, 60) and np.all(sd[0] >= d[0] - 1e-12)       # a vertex is a point of its triangle
