@@ -25,7 +25,7 @@ __device__ __forceinline__ float tri_closest_sq(const float* __restrict__ t, flo
         float d3 = abx * bpx + aby * bpy + abz * bpz, d4 = acx * bpx + acy * bpy + acz * bpz;
         if (d3 >= 0.f && d4 <= d3) { type = 2; qx = t[3]; qy = t[4]; qz = t[5]; }
         else {
-            float vc = d1 * d4 - d3 * d2;
+            float vc = xmul(d1, d4) - xmul(d3, d2);      // rounded products: an FMA here leaves a residual on degenerate (b == c) faces
             if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) {
                 float v = d1 / (d1 - d3);
                 type = 4; qx = t[0] + v * abx; qy = t[1] + v * aby; qz = t[2] + v * abz;
@@ -34,12 +34,12 @@ __device__ __forceinline__ float tri_closest_sq(const float* __restrict__ t, flo
                 float d5 = abx * cpx + aby * cpy + abz * cpz, d6 = acx * cpx + acy * cpy + acz * cpz;
                 if (d6 >= 0.f && d5 <= d6) { type = 3; qx = t[6]; qy = t[7]; qz = t[8]; }
                 else {
-                    float vb = d5 * d2 - d1 * d6;
+                    float vb = xmul(d5, d2) - xmul(d1, d6);
                     if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) {
                         float w = d2 / (d2 - d6);
                         type = 6; qx = t[0] + w * acx; qy = t[1] + w * acy; qz = t[2] + w * acz;
                     } else {
-                        float va = d3 * d6 - d5 * d4;
+                        float va = xmul(d3, d6) - xmul(d5, d4);
                         if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
                             float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
                             type = 5; qx = t[3] + w * (t[6] - t[3]); qy = t[4] + w * (t[7] - t[4]); qz = t[5] + w * (t[8] - t[5]);
