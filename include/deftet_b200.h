@@ -351,6 +351,19 @@ int dtb_project_faces_backward(const float* pos, const float* feat, const int32_
 int dtb_point_to_mesh_distance(const float* points, const float* face_vertices, int B, int P, int F, float* dist,
                                long long* face_idx, int32_t* dist_type, void* stream);
 
+/* ---- N2: graph-convolution neighbourhood product on the A10 adjacency ---------------------
+ * Replaces utils/matrix_utils.py:22-33 sparse_batch_matmul (torch.sparse.mm on a transposed/reshaped copy of the dense operand)
+ * as layers/gcn_decoder.py:44-56 GraphConv.forward calls it.
+ * dtb_coo_to_csr: COO triplets (int64 row/col as torch sparse tensors hold them, f32 values, any order) -> CSR of the matrix
+ *   (transpose = 0) or of its transpose (transpose = 1, used for the backward pass): row_ptr (n_major+1) i32, col (nnz) i32
+ *   ascending within a row, val (nnz) f32.  Set-up time (once per adjacency).
+ * dtb_spmm_csr: out (B,n_rows,p) = A @ x (B,n_cols,p) for every sample; HBM bound, 2*4*B*n*p algorithmic bytes. */
+size_t dtb_coo_to_csr_workspace(long long nnz);
+int dtb_coo_to_csr(const long long* rows, const long long* cols, const float* vals, long long nnz, int n_rows, int n_cols,
+                   int transpose, int32_t* row_ptr, int32_t* col, float* val, void* workspace, size_t workspace_bytes, void* stream);
+int dtb_spmm_csr(const int32_t* row_ptr, const int32_t* col, const float* val, const float* x, int B, int n_rows, int n_cols, int p,
+                 float* out, void* stream);
+
 /* ---- device-wide primitives (exported for the self-tests; also usable by integrators) ----------------- */
 size_t dtb_prim_scan_workspace(size_t n);
 int dtb_prim_exclusive_scan_u32(const unsigned* in, unsigned* out, size_t n, unsigned* total, void* ws, size_t ws_bytes,

@@ -38,6 +38,8 @@ def main():
         section_n3(dev, flush, peak, a.quick)
     if not only or "diffrender" in only:
         section_diffrender(dev, flush, a.quick)
+    if not only or "n2" in only:
+        section_n2(dev, flush, peak, a.quick)
     if only and "core" not in only:
         return
 
@@ -210,6 +212,36 @@ def section_n3(dev, flush, peak, quick):
         med, _ = timeit(prj, 10, 3, flush)
         by = 2 * (12 * F + F * 3 * (4 + 8 + 16)) + 28 * V * 2
         emit(row="N3 project_faces fwd+bwd (1 view, 4 features)", res=res, V=V, faces=int(F), ms=med, algorithmic_bytes=by, hbm_frac=by / (med * 1e-3) / 1e9 / peak)
+
+
+def section_n2(dev, flush, peak, quick):
+    """N2: GraphConv neighbourhood product A x on the vertex adjacency, 256-wide features (layers/gcn_decoder.py:44-56), next to
+    the reference expression (torch.sparse.mm on the transposed/reshaped operand, utils/matrix_utils.py:22-33) on the same GPU."""
+    from deftet_b200 import graph
+    for res, B in ((70, 8),) if quick else ((40, 8), (70, 8), (100, 4)):
+        g = acute_lattice_grid(res)
+        V = g.n_vert
+        tet = torch.from_numpy(g.tets).to(dev)
+        adj = builders.tet_to_adj_sparse(V, tet, normalize=True).coalesce()
+        csr = graph.csr_of(adj)
+        p = 256
+        x = torch.randn(B, V, p, device=dev)
+        by = 2 * 4 * B * V * p + 8 * csr.nnz + 4 * V
+        med, mn = timeit(lambda: graph.sparse_batch_matmul(adj, x), 10, 3, flush)
+        xg = x.clone().requires_grad_(True)
+
+        def fb():
+            xg.grad = None
+            graph.sparse_batch_matmul(adj, xg).backward(x)
+        med_fb, _ = timeit(fb, 10, 3, flush)
+
+        def ref():
+            d = x.transpose(0, 1).reshape(V, B * p)
+            return torch.sparse.mm(adj, d).reshape(V, B, p).transpose(0, 1)
+        med_ref, _ = timeit(ref, 5, 2, flush)
+        emit(row="N2 sparse_batch_matmul fwd (A x, 256 features)", res=res, batch=B, V=V, nnz=csr.nnz, ms=med, ms_min=mn, algorithmic_bytes=by,
+             hbm_frac=by / (med * 1e-3) / 1e9 / peak, achieved_gbs=by / (med * 1e-3) / 1e9, fwd_bwd_ms=med_fb,
+             reference_torch_sparse_mm_ms=med_ref, speedup_vs_torch_sparse=med_ref / med)
 
 
 def section_diffrender(dev, flush, quick):
