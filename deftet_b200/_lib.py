@@ -10,7 +10,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdeftet_b200.so")
+LIB_PATH = os.environ.get("DEFTET_B200_LIB") or os.path.join(_HERE, "libdeftet_b200.so")      # override: A/B builds of the same ABI
 
 _lib = None
 _lock = threading.Lock()

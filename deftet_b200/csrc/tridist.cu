@@ -249,12 +249,18 @@ __global__ void __launch_bounds__(256) qbin_fill_kernel(const float* __restrict_
 //   2. re-scans the candidates with a bounding-sphere reject and evaluates the few survivors.
 // A query whose best distance cannot be certified against faces outside the neighbourhood falls back to the general
 // brick walk.  Results are identical to the brute-force scan (lexicographic minimum of (distance, face id)).
-constexpr int PFD_THREADS = 64;
-#ifndef PFD_MIN_CTAS
-#define PFD_MIN_CTAS 12
+#ifndef PFD_THREADS_N
+#define PFD_THREADS_N 128
 #endif
-constexpr int PFD_CHUNK = 128;      // staged candidate capacity (< 256: survivor lists hold uint8 indices)
-constexpr int PFD_SCAN = 128;       // candidates of the 27 bricks inspected per staging round (<= PFD_CHUNK)
+constexpr int PFD_THREADS = PFD_THREADS_N;
+#ifndef PFD_MIN_CTAS
+#define PFD_MIN_CTAS 6
+#endif
+#ifndef PFD_CHUNK_N
+#define PFD_CHUNK_N 128
+#endif
+constexpr int PFD_CHUNK = PFD_CHUNK_N;      // staged candidate capacity (< 256: survivor lists hold uint8 indices)
+constexpr int PFD_SCAN = PFD_CHUNK_N;       // candidates of the 27 bricks inspected per staging round (<= PFD_CHUNK)
 constexpr int PFD_LIST = 12;        // survivors remembered per query and chunk
 
 __device__ __forceinline__ unsigned long long pack_df(float d, int f) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)f; }
@@ -331,7 +337,6 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
             v.p[0] = q.x; v.p[1] = q.y; v.p[2] = q.z;
             orig = __float_as_int(q.w);
             if (brute) { for (int f = 0; f < nf; ++f) v.face(f); }
-            else { for (int k = 0; k < na; ++k) v.face(always[(size_t)b * always_cap + k]); }
         } else { v.p[0] = v.p[1] = v.p[2] = 0.f; }
         s_q[warp][lane][0] = v.p[0]; s_q[warp][lane][1] = v.p[1]; s_q[warp][lane][2] = v.p[2];
         float ub = 3.0e38f;                                 // upper bound of the answer: a centroid is a point of its face
@@ -395,13 +400,16 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
             // ---- scan 2: remember the candidates the bounding sphere cannot reject against that bound ----
             int ns = 0;
             if (active) {
+                // a face whose centroid is farther than sqrt(bound) + rmax cannot beat the bound (it lies inside the ball
+                // (centroid, rmax)); the margins cover the rounding of this test, which only prunes and never decides
                 const float bound = fminf(ub * 1.0001f, v.best);
+                const float rr = sqrtf(bound) * 1.0002f + rmax;
+                const float thr = rr * rr * 1.0002f;
                 for (int k = 0; k < n; ++k) {
                     if (k == kn) continue;
                     float4 it = s_cen[k];
                     float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
-                    float lb = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz) - rmax, 0.f) * 0.9999f;
-                    if (lb * lb > bound) continue;
+                    if (dx * dx + dy * dy + dz * dz > thr) continue;
                     if (ns < PFD_LIST) { s_list[threadIdx.x][ns++] = (unsigned char)k; }
                     else {                                   // list full (rare): evaluate on the spot
                         const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_STRIDE);
@@ -439,6 +447,24 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
                 float d = __uint_as_float((unsigned)(pb >> 32));
                 int f = (int)(unsigned)(pb & 0xffffffffull);
                 if (active) { v.best = d; v.bi = f; }        // s_best only ever decreased from (v.best, v.bi)
+            }
+        }
+        if (active && !brute) {
+            // the "always test" faces (unreliable xy-projection / tiny: geometric pruning by the centroid is not valid for them) are
+            // looked at last, when the running minimum is tight: the reference distance is plane^2 + (in-plane term >= 0), so a face
+            // whose plane is farther than the current best cannot win; the others are evaluated from the precomputed half
+            for (int k = 0; k < na; ++k) {
+                const int f = always[(size_t)b * always_cap + k];
+                const float4* src = preb + (size_t)f * 8;
+                const float4 w2 = __ldg(src + 2), w3 = __ldg(src + 3);          // floats 9..11 = unit normal, 12 = dot(n, a)
+                const float nrm[3] = {w2.y, w2.z, w2.w};
+                const float t = xsub(w3.x, xdot(nrm, v.p));
+                if (xmul(t, t) > v.best) continue;
+                __align__(16) float buf[FACEPRE_FLOATS];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) reinterpret_cast<float4*>(buf)[m] = __ldg(src + m);
+                const float d = tri_distance_pre(*reinterpret_cast<const FacePre*>(buf), v.p);
+                if (v.best > d || (d == v.best && v.bi >= 0 && f < v.bi)) { v.best = d; v.bi = f; }
             }
         }
         if (active && !brute && nf > 0) {
