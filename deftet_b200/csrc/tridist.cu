@@ -159,19 +159,21 @@ __global__ void __launch_bounds__(256) face_stats_kernel(const float* __restrict
     float r = 0.f;
     if (f < counts[b]) {
         const float* t = soup + ((size_t)b * Fmax + f) * 9;
-        if (pre) {                                   // query-independent half of the distance, once per face
-            FacePre fp;
-            face_precompute(t, fp);
-            const float4* src = reinterpret_cast<const float4*>(&fp);
-            float4* dst = pre + ((size_t)b * Fmax + f) * 8;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) dst[m] = src[m];
-        }
         float cx = (t[0] + t[3] + t[6]) * (1.f / 3.f), cy = (t[1] + t[4] + t[7]) * (1.f / 3.f), cz = (t[2] + t[5] + t[8]) * (1.f / 3.f);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             float dx = t[k * 3] - cx, dy = t[k * 3 + 1] - cy, dz = t[k * 3 + 2] - cz;
             r = fmaxf(r, sqrtf(dx * dx + dy * dy + dz * dz));
+        }
+        if (pre) {                                   // query-independent half of the distance, once per face
+            FacePre fp;
+            face_precompute(t, fp);
+            // this face's own bounding radius around its centroid (inflated like rmax; +inf when undefined: never pruned by it)
+            fp.pad[1] = (r == r) ? r * 1.001f + 1e-7f : __int_as_float(0x7f800000);
+            const float4* src = reinterpret_cast<const float4*>(&fp);
+            float4* dst = pre + ((size_t)b * Fmax + f) * 8;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) dst[m] = src[m];
         }
         float e1[3] = {t[3] - t[0], t[4] - t[1], t[5] - t[2]}, e2[3] = {t[6] - t[0], t[7] - t[1], t[8] - t[2]};
         float nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
@@ -256,6 +258,9 @@ constexpr int PFD_THREADS = PFD_THREADS_N;
 #ifndef PFD_MIN_CTAS
 #define PFD_MIN_CTAS 6
 #endif
+#ifndef PFD_REACH_H
+#define PFD_REACH_H 1.25f
+#endif
 #ifndef PFD_CHUNK_N
 #define PFD_CHUNK_N 128
 #endif
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
     const float slack = 1e-3f * g.h + 1e-6f * (fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz) + (float)G * g.h);
     // only faces whose centroid lies within `reach` of this brick are staged; a query is final when its search ball
     // (sqrt(best) + rmax) stays inside that region, otherwise it falls back to the general walk
-    const float reach = rmax + 1.25f * g.h;
+    const float reach = rmax + PFD_REACH_H * g.h;
     const float lx0 = g.ox + (float)bx0 * bw, ly0 = g.oy + (float)by0 * bw, lz0 = g.oz + (float)bz0 * bw;
     const float rlo[3] = {lx0 - reach, ly0 - reach, lz0 - reach}, rhi[3] = {lx0 + bw + reach, ly0 + bw + reach, lz0 + bw + reach};
     const float gmax = (float)G * g.h;
@@ -400,16 +405,16 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
             // ---- scan 2: remember the candidates the bounding sphere cannot reject against that bound ----
             int ns = 0;
             if (active) {
-                // a face whose centroid is farther than sqrt(bound) + rmax cannot beat the bound (it lies inside the ball
-                // (centroid, rmax)); the margins cover the rounding of this test, which only prunes and never decides
+                // a face whose centroid is farther than sqrt(bound) + its bounding radius cannot beat the bound (it lies inside
+                // the ball (centroid, radius)); the margins cover the rounding of this test, which only prunes and never decides
                 const float bound = fminf(ub * 1.0001f, v.best);
-                const float rr = sqrtf(bound) * 1.0002f + rmax;
-                const float thr = rr * rr * 1.0002f;
+                const float sb = sqrtf(bound) * 1.0002f;
                 for (int k = 0; k < n; ++k) {
                     if (k == kn) continue;
                     float4 it = s_cen[k];
                     float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
-                    if (dx * dx + dy * dy + dz * dz > thr) continue;
+                    const float rr = sb + fminf(s_pre[(size_t)k * FACEPRE_STRIDE + (FACEPRE_FLOATS - 1)], rmax);   // the face's own radius
+                    if (dx * dx + dy * dy + dz * dz > rr * rr * 1.0002f) continue;
                     if (ns < PFD_LIST) { s_list[threadIdx.x][ns++] = (unsigned char)k; }
                     else {                                   // list full (rare): evaluate on the spot
                         const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_STRIDE);
