@@ -556,13 +556,15 @@ def roofline_pass(eng, step, scenes, uv, B, T, V, P, S, Fmax, S_face, NSETS, ite
     ms, by = kms[name], kbytes[name]
     achieved = by / (ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic.get(name), "peak_source": peak_src, "algorithmic_bytes": by, "ms": ms,
+            "traffic": traffic.get(name), "sm_throughput_pct_ncu": traffic.get(name + ".sm_throughput_pct"), "peak_source": peak_src,
+            "algorithmic_bytes": by, "ms": ms,
             "kernels_ms": {k: round(v, 4) for k, v in kms.items()},
             "kernels_frac": {k: round(kbytes[k] / (v * 1e-3) / 1e9 / peak, 4) for k, v in kms.items()},
             "groups_ms": {k: round(v[0], 4) for k, v in groups.items()},
             "groups_frac": {k: round(v[1] / (v[0] * 1e-3) / 1e9 / peak, 4) for k, v in groups.items()},
             "note": "search kernels are instruction/latency bound (exact-semantics fp32 predicates on binned candidates): DRAM traffic is "
-                    "1-3 % of peak in the ncu captures (profiles/); algorithmic bytes per DESIGN.md section 4"}
+                    "1-3 % of peak in the ncu captures (profiles/), sm_throughput_pct_ncu is the SM pipe utilisation of the same capture; "
+                    "algorithmic bytes per DESIGN.md section 4"}
     launches = count_launches(step, scenes, uv)
     return roof, launches
 

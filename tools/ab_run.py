@@ -42,7 +42,7 @@ def child(op):
     elif op == "nn":
         def fn():
             k = state["k"] % 2; state["k"] += 1
-            return surface.surface_chamfer(scs[k]["pos"], fcs[k][0], fcs[k][1], u, v, scs[k]["gt"])
+            return surface.surface_chamfer(scs[k]["pos"], fcs[k][0], fcs[k][1], u, v, scs[k]["gt"], int(os.environ.get("DTB_AB_G", "0")))
         for k in range(2):
             q = scs[k]["gt"] + 0.01
             h.update(search.nearest_neighbor_index(q, scs[k]["gt"]).cpu().numpy().tobytes())
@@ -55,7 +55,7 @@ def child(op):
             c, w = search.point_in_tet(scs[k]["pos"], eng.tet, scs[k]["pts"])
             h.update(c.cpu().numpy().tobytes()); h.update(w.cpu().numpy().tobytes())
     med, mn = timeit(fn, 20, 4, flush)
-    print(json.dumps({"op": op, "lib": os.path.basename(os.environ.get("DEFTET_B200_LIB", "default")), "ms_median": med, "ms_min": mn, "sha1": h.hexdigest()[:16]}))
+    print(json.dumps({"op": op, "lib": os.path.basename(os.environ.get("DEFTET_B200_LIB", "default")), "G": os.environ.get("DTB_AB_G", "auto"), "ms_median": med, "ms_min": mn, "sha1": h.hexdigest()[:16]}))
 
 
 if __name__ == "__main__":
@@ -65,6 +65,8 @@ if __name__ == "__main__":
         op = sys.argv[1]
         for name in sys.argv[2:]:
             env = dict(os.environ)
+            if "@" in name:                      # name@G: grid resolution override for the op
+                name, env["DTB_AB_G"] = name.split("@")
             if name != "default":
                 env["DEFTET_B200_LIB"] = os.path.join(ROOT, "build", "variants", "lib_%s.so" % name)
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", op], env=env, capture_output=True, text=True)
