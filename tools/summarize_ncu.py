@@ -23,15 +23,17 @@ def short(name):
     return name.split("(")[0].strip()
 
 
-def launches(path, out, command, note):
+def launches(path, out, command, note, marker="energies_fwd_kernel"):
     rows = [r for r in csv.reader(open(path)) if r]
     start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
     hdr = rows[start]
     ki, mi, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     agg = OrderedDict()
-    for r in rows[start + 1:]:
-        if len(r) <= vi or r[mi] != "gpu__time_duration.sum":
-            continue
+    data = [r for r in rows[start + 1:] if len(r) > vi and r[mi] == "gpu__time_duration.sum"]
+    marks = [i for i, r in enumerate(data) if marker and marker in r[ki]]
+    if len(marks) >= 5:                       # one complete step: from the 4th to the 5th launch of the marker kernel
+        data = data[marks[3]:marks[4]]
+    for r in data:
         v = float(r[vi].replace(",", ""))
         v = v / 1e3 if r[ui] in ("ns", "nsecond") else v
         k = short(r[ki])
