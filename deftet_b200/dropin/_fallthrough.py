@@ -13,3 +13,17 @@ def extend(pkg_path, name):
         cand = os.path.join(root, name)
         if os.path.isdir(cand) and cand not in pkg_path:
             pkg_path.append(cand)
+
+
+def exec_reference_init(namespace, name):
+    """Run the reference package's own ``__init__.py`` inside the shadowing package (its imports resolve through the extended
+    ``__path__``, this tree first).  Returns False when no checkout is configured."""
+    root = os.environ.get("DEFTET_REFERENCE_ROOT")
+    if not root:
+        return False
+    init = os.path.join(root, name, "__init__.py")
+    if not os.path.isfile(init):
+        return False
+    with open(init) as f:
+        exec(compile(f.read(), init, "exec"), namespace)
+    return True

@@ -351,6 +351,29 @@ int dtb_project_faces_backward(const float* pos, const float* feat, const int32_
 int dtb_point_to_mesh_distance(const float* points, const float* face_vertices, int B, int P, int F, float* dist,
                                long long* face_idx, int32_t* dist_type, void* stream);
 
+/* ---- N4 (second half): voxel-feature sampling at grid vertices / tet centroids ---------
+ * Replaces layers/pv_module/functional/devoxelization.py:47-53 trilinear_devoxelize -- the live definition: normalise
+ * (coords*2+1)/r-1, flip, torch F.grid_sample(bilinear, padding_mode='border', align_corners=False) -- as
+ * layers/pc_model.py:182-194 sample_f calls it per encoder level, and its autograd.
+ * feat (B,C,R,R,R) f32 contiguous.  coords: voxel coordinates, element (b,k,n) at coords[b*cs_b + k*cs_k + n*cs_n]
+ * ((B,3,N) contiguous = strides 3N, N, 1; the reference passes a permuted view = 3N, 1, 3).  With
+ * DTB_DEVOX_FROM_POSITIONS the same array holds positions p and the kernel applies sample_f's own prelude
+ * c = clamp((p + 0.5) * R, 0, R - 1) (pc_model.py:186-191), including its gradient.
+ * out (B,C,N): element (b,c,n) at out[b*out_batch_stride + c*N + n] (out_batch_stride > C*N writes a channel slice of the
+ * concatenated sample_f tensor in place).
+ * backward: grad_out laid out like out.  grad_feat (B,C,R^3) is OVERWRITTEN (NULL to skip); grad_coords has the strides of
+ * coords and is ACCUMULATED into (the caller zeroes it once for all levels; NULL to skip; needs feat).
+ * DTB_DEVOX_GLOBAL_GATHER forces the no-staging kernels that serve R > 36; DTB_DEVOX_SIMPLE selects the one-point-per-thread
+ * kernels instead of the four-points-per-thread ones (both for self-tests and A/B timing; same results). */
+#define DTB_DEVOX_FROM_POSITIONS 1
+#define DTB_DEVOX_GLOBAL_GATHER 2
+#define DTB_DEVOX_SIMPLE 4
+int dtb_trilinear_devoxelize_forward(const float* feat, const float* coords, long long cs_b, long long cs_k, long long cs_n, int B,
+                                     int C, int N, int R, int flags, float* out, long long out_batch_stride, void* stream);
+int dtb_trilinear_devoxelize_backward(const float* feat, const float* coords, long long cs_b, long long cs_k, long long cs_n,
+                                      const float* grad_out, long long grad_out_batch_stride, int B, int C, int N, int R, int flags,
+                                      float* grad_feat, float* grad_coords, void* stream);
+
 /* ---- N2: graph-convolution neighbourhood product on the A10 adjacency ---------------------
  * Replaces utils/matrix_utils.py:22-33 sparse_batch_matmul (torch.sparse.mm on a transposed/reshaped copy of the dense operand)
  * as layers/gcn_decoder.py:44-56 GraphConv.forward calls it.

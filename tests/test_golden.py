@@ -206,3 +206,39 @@ def test_metrics_oracle_point_triangle_distance_is_a_true_minimum():
     assert np.allclose(np.sqrt(d[0]), np.sqrt(ds.min(-1)), atol=2.0 / n)
     sd, si = orc_m.sided_distance(pts, fv[:, :, 0])
     assert sd.shape == (1, 60) and np.all(sd[0] >= d[0] - 1e-12)       # a vertex is a point of its triangle
+
+
+# ---- N4 second half: voxel-feature sampling -------------------------------------------------------------------------------------
+DEVOX_CASES = (("r32", 32), ("r16", 16), ("r8", 8), ("r5_odd", 5), ("r40_big", 40))
+
+
+def test_devox_oracle_matches_reference_function():
+    """oracle/devox.py vs the outputs of the reference's own trilinear_devoxelize (tests/golden/make_golden_devox.py): the numpy
+    restatement is bit-identical in the forward pass; the differentiable restatement reproduces its autograd."""
+    import torch
+    from oracle import devox as od
+    g = np.load(os.path.join(GOLD, "devox.npz"))
+    for name, R in DEVOX_CASES:
+        feat, coords = g[name + "_feat"], g[name + "_coords"]
+        assert np.array_equal(od.trilinear_devoxelize(feat, coords, R), g[name + "_out"]), name
+        ft, ct = torch.tensor(feat, requires_grad=True), torch.tensor(coords, requires_grad=True)
+        o = od.trilinear_devoxelize_torch(ft, ct, R)
+        gf, gc = torch.autograd.grad(o, (ft, ct), torch.tensor(g[name + "_grad_out"]))
+        assert np.abs(gf.numpy() - g[name + "_grad_feat"]).max() <= 1e-5 * max(1.0, np.abs(g[name + "_grad_feat"]).max()), name
+        assert np.abs(gc.numpy() - g[name + "_grad_coords"]).max() <= 1e-5 * max(1.0, np.abs(g[name + "_grad_coords"]).max()), name
+        # the border clip really is exercised: some coordinates carry no gradient
+        assert (g[name + "_grad_coords"] == 0).any() and (g[name + "_grad_coords"] != 0).any()
+
+
+def test_devox_oracle_sample_f_matches_reference():
+    import torch
+    from oracle import devox as od
+    g = np.load(os.path.join(GOLD, "devox.npz"))
+    pos = torch.tensor(g["sf_pos"], requires_grad=True)
+    cl = [torch.tensor(g["sf_feat%d" % i], requires_grad=True) for i in range(3)]
+    o = od.sample_f(pos, cl)
+    assert np.array_equal(o.detach().numpy(), g["sf_out"])
+    grads = torch.autograd.grad(o, [pos] + cl, torch.tensor(g["sf_grad_out"]))
+    assert np.abs(grads[0].numpy() - g["sf_grad_pos"]).max() <= 1e-5 * np.abs(g["sf_grad_pos"]).max()
+    for i in range(3):
+        assert np.abs(grads[1 + i].numpy() - g["sf_grad_feat%d" % i]).max() <= 1e-5 * max(1.0, np.abs(g["sf_grad_feat%d" % i]).max())

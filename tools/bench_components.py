@@ -40,6 +40,8 @@ def main():
         section_diffrender(dev, flush, a.quick)
     if not only or "n2" in only:
         section_n2(dev, flush, peak, a.quick)
+    if not only or "devox" in only:
+        section_devox(dev, flush, peak, a.quick)
     if only and "core" not in only:
         return
 
@@ -242,6 +244,68 @@ def section_n2(dev, flush, peak, quick):
         emit(row="N2 sparse_batch_matmul fwd (A x, 256 features)", res=res, batch=B, V=V, nnz=csr.nnz, ms=med, ms_min=mn, algorithmic_bytes=by,
              hbm_frac=by / (med * 1e-3) / 1e9 / peak, achieved_gbs=by / (med * 1e-3) / 1e9, fwd_bwd_ms=med_fb,
              reference_torch_sparse_mm_ms=med_ref, speedup_vs_torch_sparse=med_ref / med)
+
+
+def section_devox(dev, flush, peak, quick):
+    """N4 (second half): sample_f = trilinear_devoxelize over the three encoder levels of layers/pc_model.py:50 at the grid's vertex
+    count (train: decode_pos) and at the tet centroids (inference: decode_occ without the 10 000-centroid mask), next to the
+    reference expression itself -- torch F.grid_sample per level + torch.cat -- on the same GPU."""
+    from deftet_b200 import devox
+    levels = [(64, 32), (128, 16), (512, 8)]
+    ctot = sum(c for c, _ in levels)
+    for res, B, what in ((70, 8, "vertices"),) if quick else ((40, 8, "vertices"), (70, 8, "vertices"), (70, 2, "centroids")):
+        g = acute_lattice_grid(res)
+        pts = g.centred() if what == "vertices" else g.centred()[g.tets.reshape(-1)].reshape(-1, 4, 3).mean(axis=1)
+        N = pts.shape[0]
+        pos = torch.from_numpy(pts.astype(np.float32)).to(dev).unsqueeze(0).repeat(B, 1, 1)
+        pos = (pos + 0.1 / res * (torch.rand_like(pos) - 0.5)).contiguous()
+        vols = [torch.randn(B, c, r, r, r, device=dev) for c, r in levels]
+        by_f = 4 * B * ctot * N + sum(4 * B * c * r ** 3 for c, r in levels) + 12 * B * N
+        med, mn = timeit(lambda: devox.sample_f(pos, vols), 10, 3, flush)
+        pg = pos.clone().requires_grad_(True)
+        vg = [v.clone().requires_grad_(True) for v in vols]
+        go = torch.randn(B, ctot, N, device=dev)
+
+        def fb():
+            pg.grad = None
+            for v in vg:
+                v.grad = None
+            devox.sample_f(pg, vg).backward(go)
+        med_fb, _ = timeit(fb, 10, 3, flush)
+        med_f_feat, _ = timeit(lambda: torch.autograd.grad(devox.sample_f(pos, vg), vg, go), 10, 3, flush)      # fwd + d/d volume only
+        med_f_pos, _ = timeit(lambda: torch.autograd.grad(devox.sample_f(pg, vols), pg, go), 10, 3, flush)      # fwd + d/d positions only
+        med_simple, _ = timeit(lambda: devox.sample_f(pos, vols, devox.SIMPLE), 10, 3, flush)
+
+        def fb_simple():
+            pg.grad = None
+            for v in vg:
+                v.grad = None
+            devox.sample_f(pg, vg, devox.SIMPLE).backward(go)
+        med_fb_simple, _ = timeit(fb_simple, 5, 2, flush)
+
+        def ref_expr(p, vs):
+            pt = (p + 0.5).permute(0, 2, 1)
+            outs = []
+            for v in vs:
+                r = v.shape[-1]
+                c = torch.clamp(pt * r, 0, r - 1)
+                c = (c * 2 + 1.0) / r - 1.0
+                grid = torch.flip(c.permute(0, 2, 1).reshape(B, 1, 1, -1, 3), dims=[-1])
+                outs.append(torch.nn.functional.grid_sample(v, grid, padding_mode='border', align_corners=False).squeeze(2).squeeze(2))
+            return torch.cat(outs, dim=1)
+        med_ref, _ = timeit(lambda: ref_expr(pos, vols), 5, 2, flush)
+
+        def ref_fb():
+            pg.grad = None
+            for v in vg:
+                v.grad = None
+            ref_expr(pg, vg).backward(go)
+        med_ref_fb, _ = timeit(ref_fb, 5, 2, flush)
+        emit(row="N4 sample_f fwd (trilinear_devoxelize x3 levels, 704 ch) at %s" % what, res=res, batch=B, N=N, ms=med, ms_min=mn,
+             algorithmic_bytes=by_f, hbm_frac=by_f / (med * 1e-3) / 1e9 / peak, achieved_gbs=by_f / (med * 1e-3) / 1e9, fwd_bwd_ms=med_fb,
+             bwd_algorithmic_bytes=by_f + 12 * B * N, reference_torch_grid_sample_ms=med_ref, reference_torch_grid_sample_fwd_bwd_ms=med_ref_fb,
+             speedup_fwd=med_ref / med, speedup_fwd_bwd=med_ref_fb / med_fb, fwd_plus_grad_volume_ms=med_f_feat, fwd_plus_grad_positions_ms=med_f_pos,
+             one_point_per_thread_kernels_ms=med_simple, one_point_per_thread_kernels_fwd_bwd_ms=med_fb_simple)
 
 
 def section_diffrender(dev, flush, quick):
