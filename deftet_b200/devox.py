@@ -16,6 +16,7 @@ from . import _lib
 FROM_POSITIONS = 1
 GLOBAL_GATHER = 2     # the no-staging kernels that serve R > 36
 SIMPLE = 4            # one point per thread instead of four (self-tests, A/B timing)
+NO_OWNER = 8          # volume gradient: the shared-atomic kernel also where the channel-owner kernel applies (R^3 <= 512)
 
 
 @_lib.register_signatures

@@ -364,10 +364,12 @@ int dtb_point_to_mesh_distance(const float* points, const float* face_vertices, 
  * backward: grad_out laid out like out.  grad_feat (B,C,R^3) is OVERWRITTEN (NULL to skip); grad_coords has the strides of
  * coords and is ACCUMULATED into (the caller zeroes it once for all levels; NULL to skip; needs feat).
  * DTB_DEVOX_GLOBAL_GATHER forces the no-staging kernels that serve R > 36; DTB_DEVOX_SIMPLE selects the one-point-per-thread
- * kernels instead of the four-points-per-thread ones (both for self-tests and A/B timing; same results). */
+ * kernels instead of the four-points-per-thread ones; DTB_DEVOX_NO_OWNER chooses the volume-gradient kernel
+ * (all for self-tests and A/B timing; same results up to summation order). */
 #define DTB_DEVOX_FROM_POSITIONS 1
 #define DTB_DEVOX_GLOBAL_GATHER 2
 #define DTB_DEVOX_SIMPLE 4
+#define DTB_DEVOX_NO_OWNER 8      /* volume gradient: not the channel-owner kernel (R^3 <= 512) but the shared-atomic one */
 int dtb_trilinear_devoxelize_forward(const float* feat, const float* coords, long long cs_b, long long cs_k, long long cs_n, int B,
                                      int C, int N, int R, int flags, float* out, long long out_batch_stride, void* stream);
 int dtb_trilinear_devoxelize_backward(const float* feat, const float* coords, long long cs_b, long long cs_k, long long cs_n,

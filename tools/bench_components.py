@@ -301,6 +301,18 @@ def section_devox(dev, flush, peak, quick):
                 v.grad = None
             ref_expr(pg, vg).backward(go)
         med_ref_fb, _ = timeit(ref_fb, 5, 2, flush)
+        # volume gradient alone, per level and per kernel choice (0 = default, NO_OWNER); random order = worst case for runs
+        per_level = {}
+        for order in ("lattice", "shuffled"):
+            p_use = pos if order == "lattice" else pos[:, torch.randperm(N, device=dev)].contiguous()
+            for c, r in levels:
+                v = torch.randn(B, c, r, r, r, device=dev, requires_grad=True)
+                gl = torch.randn(B, c, N, device=dev)
+                for fl, tag in ((0, "default"), (devox.NO_OWNER, "shared_atomics")):
+                    o = devox.sample_f(p_use, [v], fl)
+                    t_, _ = timeit(lambda: torch.autograd.grad(o, v, gl, retain_graph=True), 10, 3, flush)
+                    per_level["%s_R%d_C%d_%s" % (order, r, c, tag)] = round(t_, 4)
+        emit(row="N4 sample_f volume-gradient kernels at %s" % what, res=res, batch=B, N=N, grad_volume_ms=per_level)
         emit(row="N4 sample_f fwd (trilinear_devoxelize x3 levels, 704 ch) at %s" % what, res=res, batch=B, N=N, ms=med, ms_min=mn,
              algorithmic_bytes=by_f, hbm_frac=by_f / (med * 1e-3) / 1e9 / peak, achieved_gbs=by_f / (med * 1e-3) / 1e9, fwd_bwd_ms=med_fb,
              bwd_algorithmic_bytes=by_f + 12 * B * N, reference_torch_grid_sample_ms=med_ref, reference_torch_grid_sample_fwd_bwd_ms=med_ref_fb,
