@@ -20,6 +20,7 @@
 //                      float atomicAdd on shared memory is a CAS loop (ATOMS.CAST.SPIN) and would serialise on such runs
 // R^3 planes that do not fit in shared memory (R > 36) fall back to *_global kernels that gather through L2.
 #include "common.cuh"
+#include "prims.cuh"
 #include "deftet_b200.h"
 
 namespace dtb {
@@ -718,6 +719,113 @@ __global__ void __launch_bounds__(64) devox_scatter_owner_kernel(DevoxArgs a, co
     }
 }
 
+// ---- grad_feat from points sorted by voxel -------------------------------------------------------------------------------------------
+// With a workspace the reduction needs neither atomics on shared memory nor an accumulation tile: the points of all samples are
+// radix-sorted once by (sample, low-corner voxel) -- stable, so a voxel lists its points in ascending index -- and a warp then walks a
+// block of 128 sorted points for 32 channels (lane = channel), keeps the 8 corner sums of the current voxel in registers and sends them
+// to HBM as reductions when the voxel changes: 8 REDs per (voxel, 32 channels) instead of 8 shared-memory read-modify-writes per run of
+// the unsorted order.  No shared tile means full occupancy, which is what the channel-owner kernel lacks (three warps per SM).
+// The gradient values of a tile of 32 points are fetched with lane = point (consecutive points of a voxel are mostly consecutive in
+// memory: a few sectors per request) and turned round through a 32 x 33 shared tile; the point records are worked out by lane = point too.
+static const int DV_SR_WARPS = 8;
+static const int DV_SR_PTS = 128;      // sorted points per warp
+
+__global__ void __launch_bounds__(256) devox_sort_keys_kernel(DevoxArgs a, long long total, unsigned long long* __restrict__ keys,
+                                                             unsigned* __restrict__ vals) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int b = (int)(i / a.N), n = (int)(i - (long long)b * a.N);
+    const DvPoint p = dv_point(a, b, n);
+    keys[i] = (unsigned long long)b * (unsigned)a.R3 + (unsigned)p.base;
+    vals[i] = (unsigned)i;
+}
+
+__global__ void __launch_bounds__(32 * DV_SR_WARPS) devox_sorted_reduce_kernel(DevoxArgs a, const unsigned long long* __restrict__ keys,
+                                                                               const unsigned* __restrict__ vals, long long total,
+                                                                               const float* __restrict__ gout, long long ob,
+                                                                               float* __restrict__ grad_feat) {
+    __shared__ float s_g[DV_SR_WARPS][32][33];
+    __shared__ __align__(16) float s_w[DV_SR_WARPS][32][8];
+    __shared__ int s_key[DV_SR_WARPS][32];
+    __shared__ int s_hib[DV_SR_WARPS][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long i0 = ((long long)blockIdx.x * DV_SR_WARPS + wid) * DV_SR_PTS;
+    if (i0 >= total) return;                                   // warps are independent: no CTA-wide barrier below
+    const long long i1 = min(total, i0 + (long long)DV_SR_PTS);
+    const int c0 = blockIdx.y * 32;
+    const int ncc = min(32, a.C - c0);
+    float (*tg)[33] = s_g[wid];
+    const float4* tw = reinterpret_cast<const float4*>(s_w[wid]);
+    const int* tk = s_key[wid];
+    const int* th = s_hib[wid];
+    const int RR = a.R * a.R;
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = 0.f;
+    int cur = -1, hcur = 0;
+
+    auto flush = [&]() {
+        const int b = cur / a.R3;
+        const int cell = cur - b * a.R3;
+        if (lane < ncc) {
+            float* dst = grad_feat + ((size_t)b * a.C + c0 + lane) * a.R3 + cell;
+            atomicAdd(dst, s[0]);
+            if (hcur & 1) atomicAdd(dst + 1, s[1]);
+            if (hcur & 2) atomicAdd(dst + a.R, s[2]);
+            if ((hcur & 3) == 3) atomicAdd(dst + a.R + 1, s[3]);
+            if (hcur & 4) {
+                atomicAdd(dst + RR, s[4]);
+                if (hcur & 1) atomicAdd(dst + RR + 1, s[5]);
+                if (hcur & 2) atomicAdd(dst + RR + a.R, s[6]);
+                if ((hcur & 3) == 3) atomicAdd(dst + RR + a.R + 1, s[7]);
+            }
+        }
+    };
+
+    for (long long it = i0; it < i1; it += 32) {
+        const long long i = it + lane;
+        int key = -1;
+        if (i < i1) {
+            key = (int)keys[i];
+            const unsigned v = vals[i];
+            const int b = (int)(v / (unsigned)a.N), n = (int)(v - (unsigned)b * (unsigned)a.N);
+            const DvPoint p = dv_point(a, b, n);
+            float w[8];
+            dv_weights(p, w);
+            float4* wd = reinterpret_cast<float4*>(s_w[wid][lane]);
+            wd[0] = make_float4(w[0], w[1], w[2], w[3]);
+            wd[1] = make_float4(w[4], w[5], w[6], w[7]);
+            s_hib[wid][lane] = dv_hib(p);
+            const float* src = gout + (size_t)b * ob + (size_t)c0 * a.N + n;
+            if (ncc == 32) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) tg[lane][c] = src[(size_t)c * a.N];
+            } else {
+                for (int c = 0; c < ncc; ++c) tg[lane][c] = src[(size_t)c * a.N];
+            }
+        }
+        s_key[wid][lane] = key;
+        __syncwarp();
+        const int cnt = (int)min(32LL, i1 - it);
+#pragma unroll 4
+        for (int p = 0; p < cnt; ++p) {
+            const int k = tk[p];
+            if (k != cur) {                                    // warp-uniform
+                if (cur >= 0) flush();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) s[q] = 0.f;
+                cur = k; hcur = th[p];
+            }
+            const float4 wa = tw[2 * p], wb = tw[2 * p + 1];
+            const float g = tg[p][lane];
+            s[0] = fmaf(wa.x, g, s[0]); s[1] = fmaf(wa.y, g, s[1]); s[2] = fmaf(wa.z, g, s[2]); s[3] = fmaf(wa.w, g, s[3]);
+            s[4] = fmaf(wb.x, g, s[4]); s[5] = fmaf(wb.y, g, s[5]); s[6] = fmaf(wb.z, g, s[6]); s[7] = fmaf(wb.w, g, s[7]);
+        }
+        __syncwarp();
+    }
+    if (cur >= 0) flush();
+}
+
 // ---- planes too large for shared memory: gather / scatter through L2 ------------------------------------------------------------
 // one thread per (b, n), channels in the loop; mode 0 forward, 1 grad coords, 2 grad feat (global reductions)
 template <int MODE>
@@ -864,6 +972,26 @@ static DevoxOwnerPlan devox_owner_plan(int B, int C, int N, int R, int flags) {
     return pl;
 }
 
+// The sorted reduction pays off when a voxel collects several points (its 8 reductions per 32 channels are amortised over them).
+static bool devox_sorted_ok(int B, int C, int N, int R, int flags) {
+    if (flags & (DTB_DEVOX_SIMPLE | DTB_DEVOX_GLOBAL_GATHER | DTB_DEVOX_NO_SORT)) return false;
+    const long long R3 = (long long)R * R * R, total = (long long)B * N;
+    if (total <= 0 || C <= 0 || total >= (1LL << 31) || (long long)B * R3 >= (1LL << 31)) return false;
+    return (flags & DTB_DEVOX_FORCE_SORT) || (long long)N >= 8 * R3;
+}
+
+struct DevoxSortBufs { unsigned long long *keys_in, *keys_out; unsigned *vals_in, *vals_out; void* sort_ws; size_t sort_ws_bytes; };
+
+static size_t devox_sorted_carve(Workspace& ws, long long total, DevoxSortBufs& sb) {
+    sb.keys_in = ws.take<unsigned long long>((size_t)total);
+    sb.keys_out = ws.take<unsigned long long>((size_t)total);
+    sb.vals_in = ws.take<unsigned>((size_t)total);
+    sb.vals_out = ws.take<unsigned>((size_t)total);
+    sb.sort_ws_bytes = sort_workspace_bytes((size_t)total);
+    sb.sort_ws = ws.take<char>(sb.sort_ws_bytes);
+    return ws.off;
+}
+
 template <typename K>
 static int devox_allow_smem(K kernel, size_t smem) {
     if (smem > 48 * 1024) DTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DV_SMEM_MAX));
@@ -931,9 +1059,24 @@ extern "C" int dtb_trilinear_devoxelize_forward(const float* feat, const float* 
     return DTB_OK;
 }
 
+extern "C" size_t dtb_trilinear_devoxelize_backward_workspace(int B, int C, int N, int R, int flags) {
+    if (B < 0 || C < 0 || N < 0 || R < 1 || R > 1024 || !devox_sorted_ok(B, C, N, R, flags)) return 0;
+    Workspace ws(nullptr, 0);
+    DevoxSortBufs sb;
+    return devox_sorted_carve(ws, (long long)B * N, sb);
+}
+
 extern "C" int dtb_trilinear_devoxelize_backward(const float* feat, const float* coords, long long cs_b, long long cs_k, long long cs_n,
                                                  const float* grad_out, long long grad_out_batch_stride, int B, int C, int N, int R,
                                                  int flags, float* grad_feat, float* grad_coords, void* stream) {
+    return dtb_trilinear_devoxelize_backward_ws(feat, coords, cs_b, cs_k, cs_n, grad_out, grad_out_batch_stride, B, C, N, R, flags, grad_feat,
+                                                grad_coords, nullptr, 0, stream);
+}
+
+extern "C" int dtb_trilinear_devoxelize_backward_ws(const float* feat, const float* coords, long long cs_b, long long cs_k, long long cs_n,
+                                                    const float* grad_out, long long grad_out_batch_stride, int B, int C, int N, int R,
+                                                    int flags, float* grad_feat, float* grad_coords, void* workspace, size_t workspace_bytes,
+                                                    void* stream) {
     DTB_REQUIRE(B >= 0 && C >= 0 && N >= 0 && R >= 1 && R <= 1024, "trilinear_devoxelize_backward: bad sizes B=%d C=%d N=%d R=%d", B, C, N, R);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t R3 = (size_t)R * R * R;
@@ -975,7 +1118,21 @@ extern "C" int dtb_trilinear_devoxelize_backward(const float* feat, const float*
     if (grad_feat) {
         DevoxPlan pl = devox_plan(B, C, N, R, flags, simple ? DV_SCATTER1 : DV_SCATTER4);
         DevoxOwnerPlan op = devox_owner_plan(B, C, N, R, flags);
-        if (op.ok) {
+        Workspace ws(workspace, workspace_bytes);
+        DevoxSortBufs sb{};
+        const long long total = (long long)B * N;
+        const bool sorted = workspace && devox_sorted_ok(B, C, N, R, flags) && devox_sorted_carve(ws, total, sb) <= workspace_bytes && ws.ok;
+        if (sorted) {
+            DTB_CUDA(cudaMemsetAsync(grad_feat, 0, (size_t)B * C * R3 * 4, st));
+            devox_sort_keys_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(a, total, sb.keys_in, sb.vals_in);
+            DTB_LAUNCH_CHECK("devox_sort_keys");
+            int bits = 1;
+            while (((long long)B * (long long)R3 - 1) >> bits) ++bits;
+            if (int e = radix_sort_pairs_u64(sb.keys_in, sb.vals_in, sb.keys_out, sb.vals_out, (size_t)total, bits, sb.sort_ws, sb.sort_ws_bytes, st)) return e;
+            const long long nblk = cdiv(total, (long long)DV_SR_PTS);
+            devox_sorted_reduce_kernel<<<dim3((unsigned)cdiv(nblk, (long long)DV_SR_WARPS), cdiv(C, 32)), 32 * DV_SR_WARPS, 0, st>>>(
+                a, sb.keys_out, sb.vals_out, total, grad_out, grad_out_batch_stride, grad_feat);
+        } else if (op.ok) {
             a.pts_per_cta = op.pts_per_cta;
             const int flush_atomic = op.nsplit > 1;
             if (flush_atomic) DTB_CUDA(cudaMemsetAsync(grad_feat, 0, (size_t)B * C * R3 * 4, st));

@@ -17,6 +17,8 @@ FROM_POSITIONS = 1
 GLOBAL_GATHER = 2     # the no-staging kernels that serve R > 36
 SIMPLE = 4            # one point per thread instead of four (self-tests, A/B timing)
 NO_OWNER = 8          # volume gradient: the shared-atomic kernel also where the channel-owner kernel applies (R^3 <= 512)
+NO_SORT = 16          # volume gradient: no sorted reduction (which is the default from 8 points per voxel on)
+FORCE_SORT = 32       # volume gradient: sorted reduction whatever the point count
 
 
 @_lib.register_signatures
@@ -24,6 +26,8 @@ def _devox_sigs(lib, sig):
     vp, i, ll = C.c_void_p, C.c_int, C.c_longlong
     sig("dtb_trilinear_devoxelize_forward", i, vp, vp, ll, ll, ll, i, i, i, i, i, vp, ll, vp)
     sig("dtb_trilinear_devoxelize_backward", i, vp, vp, ll, ll, ll, vp, ll, i, i, i, i, i, vp, vp, vp)
+    sig("dtb_trilinear_devoxelize_backward_workspace", C.c_size_t, i, i, i, i, i)
+    sig("dtb_trilinear_devoxelize_backward_ws", i, vp, vp, ll, ll, ll, vp, ll, i, i, i, i, i, vp, vp, vp, C.c_size_t, vp)
 
 
 def _volume(c):
@@ -42,9 +46,13 @@ def _forward_level(feat, coords, strides, N, flags, out, out_offset):
 def _backward_level(feat, coords, strides, N, flags, grad_out, go_offset, grad_feat, grad_coords):
     B, Cc, R = feat.shape[0], feat.shape[1], feat.shape[-1]
     src = C.c_void_p(grad_out.data_ptr() + 4 * go_offset)
-    _lib.check(_lib.lib().dtb_trilinear_devoxelize_backward(_lib.ptr(feat), _lib.ptr(coords), strides[0], strides[1], strides[2], src,
-                                                            grad_out.stride(0), B, Cc, N, R, flags, _lib.ptr(grad_feat), _lib.ptr(grad_coords),
-                                                            _lib.stream_ptr()), "dtb_trilinear_devoxelize_backward")
+    lib = _lib.lib()
+    # temporary memory for the sorted reduction of the volume gradient comes from torch's caching allocator (no cudaMalloc on the path)
+    ws_bytes = lib.dtb_trilinear_devoxelize_backward_workspace(B, Cc, N, R, flags) if grad_feat is not None else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feat.device) if ws_bytes else None
+    _lib.check(lib.dtb_trilinear_devoxelize_backward_ws(_lib.ptr(feat), _lib.ptr(coords), strides[0], strides[1], strides[2], src,
+                                                        grad_out.stride(0), B, Cc, N, R, flags, _lib.ptr(grad_feat), _lib.ptr(grad_coords),
+                                                        _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "dtb_trilinear_devoxelize_backward_ws")
 
 
 class _Devoxelize(torch.autograd.Function):

@@ -364,17 +364,25 @@ int dtb_point_to_mesh_distance(const float* points, const float* face_vertices, 
  * backward: grad_out laid out like out.  grad_feat (B,C,R^3) is OVERWRITTEN (NULL to skip); grad_coords has the strides of
  * coords and is ACCUMULATED into (the caller zeroes it once for all levels; NULL to skip; needs feat).
  * DTB_DEVOX_GLOBAL_GATHER forces the no-staging kernels that serve R > 36; DTB_DEVOX_SIMPLE selects the one-point-per-thread
- * kernels instead of the four-points-per-thread ones; DTB_DEVOX_NO_OWNER chooses the volume-gradient kernel
+ * kernels instead of the four-points-per-thread ones; DTB_DEVOX_NO_OWNER / NO_SORT / FORCE_SORT choose the volume-gradient kernel
  * (all for self-tests and A/B timing; same results up to summation order). */
 #define DTB_DEVOX_FROM_POSITIONS 1
 #define DTB_DEVOX_GLOBAL_GATHER 2
 #define DTB_DEVOX_SIMPLE 4
 #define DTB_DEVOX_NO_OWNER 8      /* volume gradient: not the channel-owner kernel (R^3 <= 512) but the shared-atomic one */
+#define DTB_DEVOX_NO_SORT 16      /* volume gradient: ignore the workspace (no sorted reduction) */
+#define DTB_DEVOX_FORCE_SORT 32    /* volume gradient: sorted reduction whenever a workspace is given, also below 8 points per voxel */
 int dtb_trilinear_devoxelize_forward(const float* feat, const float* coords, long long cs_b, long long cs_k, long long cs_n, int B,
                                      int C, int N, int R, int flags, float* out, long long out_batch_stride, void* stream);
 int dtb_trilinear_devoxelize_backward(const float* feat, const float* coords, long long cs_b, long long cs_k, long long cs_n,
                                       const float* grad_out, long long grad_out_batch_stride, int B, int C, int N, int R, int flags,
                                       float* grad_feat, float* grad_coords, void* stream);
+/* The same with temporary memory: the volume gradient is then computed from the points radix-sorted by voxel (no shared-memory
+ * atomics), when a voxel collects 8 points or more on average.  *_workspace returns the bytes to provide (0: not applicable). */
+size_t dtb_trilinear_devoxelize_backward_workspace(int B, int C, int N, int R, int flags);
+int dtb_trilinear_devoxelize_backward_ws(const float* feat, const float* coords, long long cs_b, long long cs_k, long long cs_n,
+                                         const float* grad_out, long long grad_out_batch_stride, int B, int C, int N, int R, int flags,
+                                         float* grad_feat, float* grad_coords, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- N2: graph-convolution neighbourhood product on the A10 adjacency ---------------------
  * Replaces utils/matrix_utils.py:22-33 sparse_batch_matmul (torch.sparse.mm on a transposed/reshaped copy of the dense operand)

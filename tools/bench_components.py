@@ -301,14 +301,14 @@ def section_devox(dev, flush, peak, quick):
                 v.grad = None
             ref_expr(pg, vg).backward(go)
         med_ref_fb, _ = timeit(ref_fb, 5, 2, flush)
-        # volume gradient alone, per level and per kernel choice (0 = default, NO_OWNER); random order = worst case for runs
+        # volume gradient alone, per level and per kernel choice (default, channel owner where it applies, shared atomics, sorted reduction); random order = worst case for runs
         per_level = {}
         for order in ("lattice", "shuffled"):
             p_use = pos if order == "lattice" else pos[:, torch.randperm(N, device=dev)].contiguous()
             for c, r in levels:
                 v = torch.randn(B, c, r, r, r, device=dev, requires_grad=True)
                 gl = torch.randn(B, c, N, device=dev)
-                for fl, tag in ((0, "default"), (devox.NO_OWNER, "shared_atomics")):
+                for fl, tag in ((0, "default"), (devox.NO_SORT, "owner"), (devox.NO_SORT | devox.NO_OWNER, "shared_atomics"), (devox.FORCE_SORT, "sorted")):
                     o = devox.sample_f(p_use, [v], fl)
                     t_, _ = timeit(lambda: torch.autograd.grad(o, v, gl, retain_graph=True), 10, 3, flush)
                     per_level["%s_R%d_C%d_%s" % (order, r, c, tag)] = round(t_, 4)
