@@ -7,7 +7,6 @@ reference glue around the brute-force C kernels of oracle/native.py.  TEST INFRA
   point_mesh_distance      utils/mesh_utils.py:368-374 (+ VarianceFunc backward, tet_analytic_distance_batch/utils.py:63-79)
   get_surface_normal_loss  utils/mesh_utils.py:16-39, get_normal :42-53
 """
-import numpy as np
 import torch
 
 from . import native

@@ -37,7 +37,7 @@ def import_reference_deftet():
 
 
 def main():
-    from deftet_b200.grid import acute_lattice_grid, read_tet_file
+    from deftet_b200.grid import read_tet_file
     from oracle import native
     from tests.util import deformed_grid
     ref_deftet = import_reference_deftet()

@@ -1,5 +1,4 @@
 """The drop-in tree resolves the reference's import paths without touching CUDA or JIT-compiling anything."""
-import importlib
 import os
 import subprocess
 import sys

@@ -1,6 +1,5 @@
 """A10-A14 parity: GPU builders vs the reference's Python twins (restated in oracle/builders.py) and, when
 oracle/_ref was built from /root/reference, vs the reference's own compiled run.so -- bit-exact."""
-import os
 
 import numpy as np
 import pytest

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
-from deftet_b200 import builders, energies, render, search, surface
+from deftet_b200 import builders, energies, render, search
 from deftet_b200.grid import acute_lattice_grid
 from tools.quick_time import timeit
 
