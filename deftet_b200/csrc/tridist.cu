@@ -264,6 +264,9 @@ constexpr int PFD_THREADS = PFD_THREADS_N;
 #ifndef PFD_CHUNK_N
 #define PFD_CHUNK_N 128
 #endif
+#ifndef PFD_PLANE_PRUNE
+#define PFD_PLANE_PRUNE 1            // scan 2 also rejects faces whose PLANE is farther than the bound (A/B: -8 % on the op, bit-identical)
+#endif
 constexpr int PFD_CHUNK = PFD_CHUNK_N;      // staged candidate capacity (< 256: survivor lists hold uint8 indices)
 constexpr int PFD_SCAN = PFD_CHUNK_N;       // candidates of the 27 bricks inspected per staging round (<= PFD_CHUNK)
 constexpr int PFD_LIST = 12;        // survivors remembered per query and chunk
@@ -415,6 +418,16 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
                     float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
                     const float rr = sb + fminf(s_pre[(size_t)k * FACEPRE_STRIDE + (FACEPRE_FLOATS - 1)], rmax);   // the face's own radius
                     if (dx * dx + dy * dy + dz * dz > rr * rr * 1.0002f) continue;
+#if PFD_PLANE_PRUNE
+                    {
+                        // the reference distance is plane^2 + (in-plane term >= 0), both formed exactly as below: a face whose plane is
+                        // farther than the bound cannot win (nor tie), whatever its in-plane term
+                        const float* fq = s_pre + (size_t)k * FACEPRE_STRIDE;
+                        const float nrm[3] = {fq[9], fq[10], fq[11]};
+                        const float t = xsub(fq[12], xdot(nrm, v.p));
+                        if (xmul(t, t) > bound) continue;
+                    }
+#endif
                     if (ns < PFD_LIST) { s_list[threadIdx.x][ns++] = (unsigned char)k; }
                     else {                                   // list full (rare): evaluate on the spot
                         const FacePre& fp = *reinterpret_cast<const FacePre*>(s_pre + (size_t)k * FACEPRE_STRIDE);
