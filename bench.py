@@ -565,6 +565,17 @@ def roofline_pass(eng, step, scenes, uv, B, T, V, P, S, Fmax, S_face, NSETS, ite
             "note": "search kernels are instruction/latency bound (exact-semantics fp32 predicates on binned candidates): DRAM traffic is "
                     "1-3 % of peak in the ncu captures (profiles/), sm_throughput_pct_ncu is the SM pipe utilisation of the same capture; "
                     "algorithmic bytes per DESIGN.md section 4"}
+    try:
+        # secondary figure for the search kernels: flops of the reference's brute-force formulation / this kernel's time,
+        # next to the FP32 peak of the chip (148 SMs x 128 lanes x 2 flop x boost clock) -- how far the binning + pruning beats a
+        # speed-of-light all-pairs kernel, since the HBM fraction says little about an ALU-bound search
+        bf = {"pit_tet_kernel": 60.0 * B * P * T, "nn_query_thread_kernel": 8.0 * B * Q * S, "pfd_forward_tiled_kernel": 120.0 * B * S * Fb}
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        roof["fp32_peak_tflops_nominal"] = round(fp32_peak, 1)
+        roof["brute_force_equivalent"] = {k: {"reference_flops": v, "tflops_equivalent": round(v / (kms[k] * 1e-3) / 1e12, 1),
+                                              "x_fp32_peak": round(v / (kms[k] * 1e-3) / 1e12 / fp32_peak, 1)} for k, v in bf.items() if k in kms}
+    except Exception as e:  # pragma: no cover  (never let a reporting extra break the bench line)
+        roof["brute_force_equivalent"] = "unavailable: %s" % e
     launches = count_launches(step, scenes, uv)
     return roof, launches
 
