@@ -49,6 +49,26 @@ def test_python_binding_declares_signatures_and_has_no_cpu_fallback():
         energies.tet_energies(torch.zeros(1, 4, 3), torch.zeros(1, 4, dtype=torch.int32), torch.zeros(1, 3, 3))
 
 
+def test_widening_rows_refuse_cpu_tensors_and_size_their_workspaces():
+    """N2 / N3 / N4 host mirrors: same rule as the hot path (no CPU emulation); host-only sizing functions are callable without a GPU."""
+    import torch
+    from deftet_b200 import _lib, devox, graph, metrics, topology  # noqa: F401
+    L = _lib.lib()
+    with pytest.raises(_lib.DeftetB200Error):
+        devox.trilinear_devoxelize(torch.zeros(1, 4, 8, 8, 8), torch.zeros(1, 3, 5), 8)
+    with pytest.raises(_lib.DeftetB200Error):
+        devox.sample_f(torch.zeros(1, 5, 3), [torch.zeros(1, 4, 8, 8, 8)])
+    with pytest.raises(_lib.DeftetB200Error):
+        metrics.sided_distance(torch.zeros(1, 5, 3), torch.zeros(1, 6, 3))
+    # volume gradient of trilinear_devoxelize: the sorted reduction asks for temporary memory from 8 points per voxel on
+    ws = L.dtb_trilinear_devoxelize_backward_workspace
+    assert ws(8, 512, 45684, 8, 0) >= 8 * 45684 * 24
+    assert ws(8, 64, 45684, 32, 0) == 0                      # 1.4 points per voxel: shared-atomic kernel, no workspace
+    assert ws(8, 64, 45684, 32, devox.FORCE_SORT) > 0
+    assert ws(8, 512, 45684, 8, devox.NO_SORT) == 0
+    assert ws(0, 512, 45684, 8, 0) == 0
+
+
 def test_run_so_shims_export_run():
     for name in ("tet_point_adj", "tet_adj_share", "tet_face_adj", "colaps_v"):
         path = os.path.join(ROOT, "deftet_b200", "dropin", "utils", "lib", name, "run.so")
