@@ -38,6 +38,45 @@ def index_vertices_by_faces(vertices_features, faces):
     return vertices_features[:, faces.reshape(-1).long()].reshape(B, faces.shape[0], 3, C_)
 
 
+def face_normals(face_vertices, unit=False):
+    """``kal.ops.mesh.face_normals``: (B,F,3,3) -> (B,F,3), (v1 - v0) x (v2 - v0), optionally normalised (dataloader.py:80-81)."""
+    n = torch.cross(face_vertices[:, :, 1] - face_vertices[:, :, 0], face_vertices[:, :, 2] - face_vertices[:, :, 0], dim=-1)
+    if unit:
+        n = n / (n.norm(dim=-1, keepdim=True) + 1e-10)
+    return n
+
+
+def face_areas(vertices, faces):
+    """``kal.ops.mesh.face_areas``: (B,V,3), (F,3) -> (B,F)."""
+    return 0.5 * face_normals(index_vertices_by_faces(vertices, faces)).norm(dim=-1)
+
+
+def sample_points(vertices, faces, num_samples, areas=None, face_features=None):
+    """``kal.ops.mesh.sample_points`` as eval.py:244-245 and dataloader.py:76-77 call it: ``num_samples`` points uniformly on the surface
+    -> (points (B,S,3), face_choices (B,S) long[, interpolated face_features (B,S,C)]).  Faces are drawn proportionally to their area,
+    the position inside a face with the recipe of the reference's own sampler (utils/mesh_utils.py:290-299: u = sqrt(rand), v = rand,
+    (1-u) a + u (1-v) b + u v c).  Plain tensor glue on the caller's device (gather + elementwise, like index_vertices_by_faces); the
+    random stream is torch's, so individual samples differ from Kaolin's while the distribution is the same (parity unpinned)."""
+    faces = faces.long()
+    B, F = vertices.shape[0], faces.shape[0]
+    if areas is None:
+        areas = face_areas(vertices, faces)
+    if F == 0 or num_samples == 0:
+        raise RuntimeError("sample_points needs at least one face and one sample")
+    w = areas.reshape(B, F).clamp(min=0) + 1e-30                     # a mesh of degenerate faces still samples (uniformly over faces)
+    face_choices = torch.multinomial(w, num_samples, replacement=True)
+    fv = index_vertices_by_faces(vertices, faces)                    # (B,F,3,3)
+    sel = torch.gather(fv, 1, face_choices.reshape(B, num_samples, 1, 1).expand(-1, -1, 3, 3))
+    u = torch.sqrt(torch.rand(B, num_samples, 1, device=vertices.device, dtype=vertices.dtype))
+    v = torch.rand(B, num_samples, 1, device=vertices.device, dtype=vertices.dtype)
+    w0, w1, w2 = 1 - u, u * (1 - v), u * v
+    points = w0 * sel[:, :, 0] + w1 * sel[:, :, 1] + w2 * sel[:, :, 2]
+    if face_features is None:
+        return points, face_choices
+    ff = torch.gather(face_features, 1, face_choices.reshape(B, num_samples, 1, 1).expand(-1, -1, 3, face_features.shape[-1]))
+    return points, face_choices, w0 * ff[:, :, 0] + w1 * ff[:, :, 1] + w2 * ff[:, :, 2]
+
+
 def point_to_mesh_distance(pointclouds, face_vertices):
     """``kal.metrics.trianglemesh.point_to_mesh_distance``: (B,P,3), (B,F,3,3) -> (squared distance (B,P), face index (B,P) long,
     distance type (B,P) int32: 0 face interior, 1-3 vertex, 4-6 edge)."""

@@ -42,3 +42,28 @@ def test_unreplaced_modules_fall_through_to_a_reference_checkout():
     assert r.returncode == 0, r.stderr[-2000:]
     lines = r.stdout.strip().splitlines()
     assert lines[0].startswith(ref) and DROPIN in lines[1]
+
+
+def test_kaolin_shim_surface_sampling_glue():
+    """kal.ops.mesh.sample_points / face_normals as eval.py:244 and dataloader.py:76-81 call them: tensor glue (no kernel), so it runs
+    here; faces are drawn in proportion to their area and every sample lies inside its face."""
+    code = ("import torch, kaolin as kal;"
+            "torch.manual_seed(0);"
+            "v = torch.tensor([[[0.,0,2],[2,0,2],[0,1,2],[0,0,2],[0,-3,2],[2,0,2]]]);"
+            "f = torch.tensor([[0,1,2],[3,4,5]]);"
+            "p, fc = kal.ops.mesh.sample_points(v, f, 40000);"
+            "assert p.shape == (1, 40000, 3) and fc.shape == (1, 40000) and fc.dtype == torch.int64;"
+            "assert abs(float((fc == 1).float().mean()) - 0.75) < 0.01;"                      # areas 1 : 3
+            "assert float((p[..., 2] - 2).abs().max()) < 1e-6;"
+            "q = p[0][fc[0] == 0];"
+            "assert bool(((q[:, 0] >= 0) & (q[:, 1] >= 0) & (q[:, 0] / 2 + q[:, 1] <= 1 + 1e-6)).all());"
+            "assert abs(float(q[:, 0].mean()) - 2 / 3) < 0.02 and abs(float(q[:, 1].mean()) - 1 / 3) < 0.01;"   # centroid of a uniform density
+            "fv = kal.ops.mesh.index_vertices_by_faces(v, f);"
+            "n = kal.ops.mesh.face_normals(fv, unit=True);"
+            "assert torch.allclose(n, torch.tensor([[[0., 0, 1], [0, 0, 1]]]), atol=1e-6);"
+            "p2, fc2, ft = kal.ops.mesh.sample_points(v, f, 100, face_features=fv);"
+            "assert torch.allclose(ft, p2, atol=1e-6);"                                        # interpolating the corners gives the point itself
+            "assert not torch.cuda.is_initialized();"
+            "print('ok')")
+    r = _run(code)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
