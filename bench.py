@@ -31,6 +31,10 @@ import torch
 from deftet_b200 import search
 
 
+PG_TIMEOUT_S = 120      # process-group timeout: a collective mismatch aborts quickly
+LOAD_STEPS = 400        # fixed number of untimed load steps before the timed region (~0.4-0.6 s at res 70 b8)
+
+
 # ------------------------------------------------------------------------------------------------- scene
 def analytic_scene(grid, B, P, S, seed, device):
     """Synthetic stand-in for one ShapeNet batch: per-sample vertex deformation, GT shape = sphere,
@@ -285,7 +289,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a mismatched collective must fail within minutes, not after NCCL's 10-minute watchdog (round-1 N=2 hang)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=PG_TIMEOUT_S))
     from deftet_b200.engine import GeometryEngine
     Fmax, S_face = 16384, 20
     eng = GeometryEngine(grid.centred(), grid.tets, max_boundary_faces=Fmax, samples_per_face=S_face, device=dev)
@@ -341,10 +347,11 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    t_load = time.perf_counter()
-    while time.perf_counter() - t_load < 0.6:      # keep the GPU under the same load while nvidia-smi collects samples
-        run(0)
-    for w in range(args.warmup):
+    if world > 1:
+        dist.barrier()
+    # Keep the GPU under the same load while nvidia-smi collects samples.  The count is FIXED: every rank must issue the
+    # same number of all-reduces (a wall-clock bound gave each rank a different count and dead-locked N=2 in round 1).
+    for w in range(LOAD_STEPS + args.warmup):
         run(w)
     torch.cuda.synchronize()
     if world > 1:
@@ -406,6 +413,12 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * B * T / (float(e2e_ms.item()) / args.steps)
+    loss_value = float(l.item())
+    if world > 1:
+        # every collective of the run is behind us: leave the process group NOW, so that the other ranks do not sit in a
+        # barrier (and run into its timeout) while rank 0 spends seconds on its single-GPU roofline / CPU legs
+        dist.barrier()
+        dist.destroy_process_group()
 
     # ---- per-kernel-group timing (eager, CUDA events) for the roofline of the dominant group -------------
     roof, launches = None, None
@@ -430,11 +443,8 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "tets/ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "reference_cuda": ref_cuda_leg,
-                "loss": float(l.item())}
+                "loss": loss_value}
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 def roofline_pass(eng, step, scenes, uv, B, T, V, P, S, Fmax, S_face, NSETS, iters=12):

@@ -42,6 +42,7 @@ class GradBucket:
             dist.all_reduce(grads[0])
             if average:
                 grads[0].div_(dist.get_world_size())
+            self.params[0].grad = grads[0]      # a rank whose grad was None still receives the other ranks' sum
             return
         if self.flat is None or self.flat.device != grads[0].device:
             self.flat = torch.empty(self.numel, device=grads[0].device, dtype=grads[0].dtype)

@@ -56,3 +56,25 @@ def test_shard_ranges_cover_batch():
             spans = [ddist.shard_range(n, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+
+
+def _worker_none_grad(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p = torch.zeros(6, requires_grad=True)
+    if rank == 1:                       # rank 0 contributes nothing: its grad stays None until the all-reduce
+        (p * torch.arange(6.0)).sum().backward()
+    ddist.GradBucket([p]).all_reduce()
+    if rank == 0:
+        torch.save(p.grad, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_single_parameter_bucket_with_missing_grad(tmp_path):
+    """the single-parameter fast path must hand the reduced sum to a rank whose grad was None."""
+    out = str(tmp_path / "g1.pt")
+    mp.spawn(_worker_none_grad, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    assert got is not None and torch.equal(got, torch.arange(6.0))
