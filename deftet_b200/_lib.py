@@ -49,6 +49,12 @@ def _declare(lib):
     sig("dtb_tet_energies_backward_soup", c_int, c_f32p, c_f32p, c_int, c_int, c_int, c_f64p, c_f32p, c_f32p, c_f32p,
         c_f32p, c_vp)
     sig("dtb_tet_inverse_v", c_int, c_f32p, c_i32p, c_int, c_int, c_f32p, c_vp)
+    sig("dtb_tet_tiles_bytes", c_sz, c_int)
+    sig("dtb_tet_tiles_build", c_int, c_i32p, c_int, c_int, c_vp, c_sz, c_i32p, c_vp)
+    sig("dtb_tet_energies_forward_tiled", c_int, c_f32p, c_i32p, c_f32p, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32p, c_f32p,
+        c_f32p, c_f64p, c_vp)
+    sig("dtb_tet_energies_backward_tiled", c_int, c_f32p, c_f32p, c_vp, c_int, c_int, c_int, c_int, c_int, c_f64p, c_f32p, c_f32p,
+        c_f32p, c_f32p, c_vp)
     for name, fn in _EXTRA_SIGS:
         fn(lib, sig)
 

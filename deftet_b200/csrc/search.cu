@@ -12,6 +12,7 @@
 //       keeps the lexicographic minimum of (distance, index) -> "strict <, lowest index wins" exactly.
 // Predicates and distances use the non-contracted fp32 sequence of the reference source (common.cuh x*),
 // so indices are bit-identical to the CPU oracle.
+#include <stdlib.h>
 #include "brickwalk.cuh"
 #include "deftet_b200.h"
 
@@ -274,6 +275,104 @@ __global__ void __launch_bounds__(128) nn_query_thread_kernel(const float* __res
     result[(size_t)b * Q + orig] = v.bi;
 }
 
+// ---- warp-cooperative walk: one CTA per (sample, brick of the target grid), one warp per chunk of 32 of the brick's queries.
+// The queries are sorted by target cell in brick-major order, so the queries of a brick are contiguous and a chunk of 32
+// of them covers a few neighbouring cells of that brick.  Every candidate point the chunk needs is loaded ONCE with a
+// warp-uniform address and evaluated by all 32 lanes (an extra candidate can only tighten a lane's minimum, never change the
+// answer), so the warp runs without divergence where the per-thread walk above kept ~9 of 32 lanes busy:
+//   phase 1  the points of the chunk's own home cells (a contiguous range of `sorted`);
+//   phase 2  every other occupied cell inside the bounding box of the lanes' search balls (capped at NN_COOP_RCAP cells),
+//            visited if ANY lane's ball reaches it (same conservative box bound as brick_walk);
+//   fallback lanes whose final ball does not fit into NN_COOP_RCAP cells finish with the per-thread brick_walk, which starts
+//            from the minimum found so far.
+// Result = lexicographic minimum of (distance, index) over a superset of every point that can attain the minimum: identical
+// to the brute-force scan of nearest_neighbor_cuda.cu:17-55.
+#ifndef NN_COOP_RCAP
+#define NN_COOP_RCAP 2.0f
+#endif
+__device__ __forceinline__ void nn_scan_range(unsigned j0, unsigned j1, const float4* __restrict__ sorted, NnVisitor& v) {
+    unsigned j = j0;
+    for (; j + 4 <= j1; j += 4) {
+        float4 a = __ldg(sorted + j), b = __ldg(sorted + j + 1), c = __ldg(sorted + j + 2), d = __ldg(sorted + j + 3);
+        v.item(a); v.item(b); v.item(c); v.item(d);
+    }
+    for (; j < j1; ++j) v.item(__ldg(sorted + j));
+}
+
+__global__ void __launch_bounds__(128) nn_query_brick_kernel(int Q, int G, const unsigned* __restrict__ bbox_ord,
+                                                             const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
+                                                             const float4* __restrict__ sorted, const unsigned long long* __restrict__ mask,
+                                                             const float4* __restrict__ qsorted, const unsigned* __restrict__ qstart,
+                                                             const unsigned* __restrict__ qend, int* __restrict__ result) {
+    const int b = blockIdx.y;
+    const int NB = G >> 2;
+    const int brick = blockIdx.x;
+    const size_t cell_base = (size_t)b * G * G * G;
+    const size_t c0 = cell_base + (size_t)brick * 64;
+    const unsigned q0 = __ldg(qstart + c0), q1 = __ldg(qend + c0 + 63);
+    if (q0 >= q1) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bx0 = brick % NB, by0 = (brick / NB) % NB, bz0 = brick / (NB * NB);
+    const GridParams g = grid_params(bbox_ord, b, G);
+    const float slack = 1e-3f * g.h + 1e-6f * (fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz) + (float)G * g.h);   // as brick_walk (inflate = 0)
+    const float shrink = slack;
+    for (unsigned base = q0 + warp * 32u; base < q1; base += 4u * 32u) {
+        const unsigned i = base + lane;
+        const bool active = i < q1;
+        float4 q = __ldg(qsorted + (active ? i : q1 - 1));
+        NnVisitor v{q.x, q.y, q.z, 1e20f, 0};
+        const int cx = cell_coord(q.x, g.ox, g.inv_h, G), cy = cell_coord(q.y, g.oy, g.inv_h, G), cz = cell_coord(q.z, g.oz, g.inv_h, G);
+        const int hloc = ((cz & 3) << 4) | ((cy & 3) << 2) | (cx & 3);            // home cell inside the brick (an inactive lane copies the last query)
+        // ---- phase 1: the chunk's home cells (sorted order => contiguous local ids) -----------------------------------------
+        const int hmin = __reduce_min_sync(0xffffffffu, hloc), hmax = __reduce_max_sync(0xffffffffu, hloc);
+        nn_scan_range(__ldg(cell_start + c0 + hmin), __ldg(cell_end + c0 + hmax), sorted, v);
+        // ---- phase 2: the cells the lanes' search balls reach -------------------------------------------------------------------
+        // Every lane searches the ball of radius rs = min(its current ball, RCAP cells); a lane that has found nothing yet
+        // searches the full RCAP ball.  A cell is skipped for a lane only if it lies outside that ball or cannot beat the
+        // lane's running minimum; the lane is COMPLETE when its final ball fits inside RCAP cells (then every cell that could
+        // hold the minimum was inside the region and was not skipped).
+        const float rcap = NN_COOP_RCAP * g.h;
+        const float rcap2 = rcap * rcap;
+        float rs = rcap;
+        if (v.best < 1e20f) rs = fminf(sqrtf(v.best) * 1.0001f + shrink + 0.01f * g.h, rcap);
+        const int x0 = max((int)floorf((q.x - rs - g.ox) * g.inv_h), 0), x1 = min((int)floorf((q.x + rs - g.ox) * g.inv_h), G - 1);
+        const int y0 = max((int)floorf((q.y - rs - g.oy) * g.inv_h), 0), y1 = min((int)floorf((q.y + rs - g.oy) * g.inv_h), G - 1);
+        const int z0 = max((int)floorf((q.z - rs - g.oz) * g.inv_h), 0), z1 = min((int)floorf((q.z + rs - g.oz) * g.inv_h), G - 1);
+        const int X0 = __reduce_min_sync(0xffffffffu, x0), X1 = __reduce_max_sync(0xffffffffu, x1);
+        const int Y0 = __reduce_min_sync(0xffffffffu, y0), Y1 = __reduce_max_sync(0xffffffffu, y1);
+        const int Z0 = __reduce_min_sync(0xffffffffu, z0), Z1 = __reduce_max_sync(0xffffffffu, z1);
+        {
+            const unsigned long long home_done = (hmax >= 63 ? ~0ull : ((1ull << (hmax + 1)) - 1ull)) & ~((1ull << hmin) - 1ull);
+            for (int bz = Z0 >> 2; bz <= (Z1 >> 2); ++bz)
+                for (int by = Y0 >> 2; by <= (Y1 >> 2); ++by)
+                    for (int bx = X0 >> 2; bx <= (X1 >> 2); ++bx) {
+                        const size_t bk = ((size_t)bz * NB + by) * NB + bx;
+                        unsigned long long m = __ldg(mask + (cell_base >> 6) + bk);
+                        if (bx == bx0 && by == by0 && bz == bz0) m &= ~home_done;
+                        if (!m) continue;
+                        // cells of this brick inside the region
+                        m &= brick_xmask(max(X0 - 4 * bx, 0), min(X1 - 4 * bx, 3)) & brick_ymask(max(Y0 - 4 * by, 0), min(Y1 - 4 * by, 3)) &
+                             brick_zmask(max(Z0 - 4 * bz, 0), min(Z1 - 4 * bz, 3));
+                        const float lx = g.ox + (float)(4 * bx) * g.h, ly = g.oy + (float)(4 * by) * g.h, lz = g.oz + (float)(4 * bz) * g.h;
+                        const size_t cb = cell_base + bk * 64;
+                        while (m) {
+                            const int k = __ffsll((long long)m) - 1;
+                            m &= m - 1;
+                            const float cxl = lx + (float)(k & 3) * g.h, cyl = ly + (float)((k >> 2) & 3) * g.h, czl = lz + (float)(k >> 4) * g.h;
+                            const bool need = !(box_dist2(q.x, q.y, q.z, cxl, cyl, czl, g.h, shrink) > fminf(v.best, rcap2));
+                            if (!__any_sync(0xffffffffu, need)) continue;
+                            nn_scan_range(__ldg(cell_start + cb + k), __ldg(cell_end + cb + k), sorted, v);
+                        }
+                    }
+        }
+        // ---- fallback: the per-thread walk for the lanes whose final ball does not fit into the searched region -----------------
+        const bool complete = (v.best < 1e20f) && (sqrtf(v.best) * 1.0001f + shrink + 0.01f * g.h <= rcap);
+        if (active && !complete)
+            brick_walk(q.x, q.y, q.z, g, G, 0.0f, cell_start, cell_end, sorted, mask, cell_base, v);
+        if (active) result[(size_t)b * Q + __float_as_int(q.w)] = v.bi;
+    }
+}
+
 // ---- interpolation of a per-vertex field at the query points through the barycentric weights ----------
 // out[b,p,:] = sum_k w[b,p,k] * field[b, tet[cond[b,p]][k], :]   (zeros where cond < 0)
 __global__ void __launch_bounds__(256) interp_fwd_kernel(const float* __restrict__ field, const int32_t* __restrict__ tet, int V, int C,
@@ -453,6 +552,11 @@ extern "C" size_t dtb_nearest_neighbor_workspace(int B, int Q, int M, int G) {
     return pointgrid_workspace_bytes(B, M, G, true, true) + 2 * align_up(cells * 4, 256) + align_up((size_t)B * Q * 4, 256) +
            align_up((size_t)B * Q * 16, 256) + scan_workspace_bytes(cells) + 512;
 }
+// DTB_NN_KERNEL=thread selects the round-1 per-thread walk (A/B measurements, tests of both kernels); default = brick kernel
+static bool nn_use_thread_walk() {
+    const char* e = getenv("DTB_NN_KERNEL");          // read per call: tests and A/B runs toggle it inside one process
+    return e && e[0] == 't';
+}
 static int nearest_neighbor_impl(const float* queries, const float* points, int32_t* result, int B, int Q, int M, int G,
                                  const int32_t* q_counts, int q_mult, void* workspace, size_t workspace_bytes, void* stream) {
     DTB_REQUIRE(B > 0 && Q >= 0 && M >= 0, "nearest_neighbor: bad sizes");
@@ -486,11 +590,17 @@ static int nearest_neighbor_impl(const float* queries, const float* points, int3
     if (rc) return rc;
     nn_qbin_fill_kernel<<<gq, 256, 0, st>>>(queries, Q, qcell, qend, qsorted);
     DTB_LAUNCH_CHECK("nn_qbin_fill");
-    dim3 grid(cdiv(Q, 128), B);
     prof_begin(PROF_NN_QUERY, st);
-    nn_query_thread_kernel<<<grid, 128, 0, st>>>(queries, Q, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask, qsorted, qstart, qend,
-                                                 q_counts, q_mult, result);
-    DTB_LAUNCH_CHECK("nn_query_thread_sorted");
+    if (nn_use_thread_walk()) {
+        dim3 grid(cdiv(Q, 128), B);
+        nn_query_thread_kernel<<<grid, 128, 0, st>>>(queries, Q, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask, qsorted, qstart, qend,
+                                                     q_counts, q_mult, result);
+        DTB_LAUNCH_CHECK("nn_query_thread_sorted");
+    } else {
+        dim3 grid((G / 4) * (G / 4) * (G / 4), B);
+        nn_query_brick_kernel<<<grid, 128, 0, st>>>(Q, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask, qsorted, qstart, qend, result);
+        DTB_LAUNCH_CHECK("nn_query_brick");
+    }
     prof_end(PROF_NN_QUERY, st);
     return DTB_OK;
 }

@@ -34,6 +34,84 @@ def tet_inverse_v(init_pos: torch.Tensor, tet: torch.Tensor) -> torch.Tensor:
     return out
 
 
+class TetTiles:
+    """Tile-local re-encoding of a tet list (csrc/energies_tiled.cu): tiles of 256 consecutive tets with their distinct
+    vertices, 2-byte local corner ids and per-vertex incidence lists.  Built once per topology on the GPU
+    (``dtb_tet_tiles_build``); the energy kernels stage vertices per tile instead of gathering 12 scalars per tet."""
+
+    def __init__(self, tet32: torch.Tensor, n_vert: int):
+        _lib.require_cuda(tet32)
+        assert tet32.dtype == torch.int32 and tet32.is_contiguous()
+        L = _lib.lib()
+        T = tet32.shape[0]
+        dev = tet32.device
+        nbytes = L.dtb_tet_tiles_bytes(T)
+        self.buf = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        nmax = torch.zeros(1, device=dev, dtype=torch.int32)
+        with torch.cuda.device(dev):
+            _lib.check(L.dtb_tet_tiles_build(_lib.ptr(tet32), T, int(n_vert), _lib.ptr(self.buf), nbytes, _lib.ptr(nmax),
+                                             _lib.stream_ptr()), "dtb_tet_tiles_build")
+        self.nloc_max = int(nmax.item())            # set-up time synchronisation (once per topology)
+        self.n_tet = T
+        self.tet = tet32
+
+
+_TILE_CACHE = {}
+
+
+def tiles_for(tet32: torch.Tensor, n_vert: int) -> TetTiles:
+    """TetTiles of a topology tensor, cached on (storage address, shape, version) -- the last 8 topologies are kept."""
+    key = (tet32.data_ptr(), tet32.shape[0], tet32._version, tet32.device.index)
+    t = _TILE_CACHE.get(key)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.DeftetB200Error("tet_energies: first use of a topology inside CUDA-graph capture; call "
+                                       "deftet_b200.energies.tiles_for(tet, n_vert) once before capturing")
+        if len(_TILE_CACHE) >= 8:
+            _TILE_CACHE.pop(next(iter(_TILE_CACHE)))
+        t = _TILE_CACHE[key] = TetTiles(tet32, n_vert)
+    return t
+
+
+def _use_direct():
+    import os
+    return os.environ.get("DTB_ENERGY_PATH", "") == "direct"      # round-1 direct-gather kernels (A/B measurements)
+
+
+class _TetEnergiesTiled(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, tet32, inv_v, flags, tiles):
+        _lib.require_cuda(pos, tet32)
+        pos = _f32c(pos)
+        B, V, _ = pos.shape
+        T = tet32.shape[0]
+        dev = pos.device
+        L = _lib.lib()
+        out = torch.zeros(3, B, device=dev, dtype=torch.float32)
+        stats = torch.empty(B, 8, device=dev, dtype=torch.float64)
+        with torch.cuda.device(dev):
+            _lib.check(L.dtb_tet_energies_forward_tiled(_lib.ptr(pos), _lib.ptr(tet32), _lib.ptr(inv_v), _lib.ptr(tiles.buf), tiles.nloc_max,
+                                                        B, V, T, flags, _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]),
+                                                        _lib.ptr(stats), _lib.stream_ptr()), "dtb_tet_energies_forward_tiled")
+        ctx.save_for_backward(pos, inv_v, stats)
+        ctx.flags, ctx.tiles, ctx.T = flags, tiles, T
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_amips, g_edge, g_vol):
+        pos, inv_v, stats = ctx.saved_tensors
+        B, V, _ = pos.shape
+        tiles = ctx.tiles
+        grad4 = torch.zeros(B, V, 4, device=pos.device, dtype=torch.float32)
+        gs = [None if g is None else _f32c(g) for g in (g_amips, g_edge, g_vol)]
+        with torch.cuda.device(pos.device):
+            _lib.check(_lib.lib().dtb_tet_energies_backward_tiled(_lib.ptr(pos), _lib.ptr(inv_v), _lib.ptr(tiles.buf), tiles.nloc_max, B, V,
+                                                                  ctx.T, ctx.flags, _lib.ptr(stats), _lib.ptr(gs[0]), _lib.ptr(gs[1]),
+                                                                  _lib.ptr(gs[2]), _lib.ptr(grad4), _lib.stream_ptr()),
+                       "dtb_tet_energies_backward_tiled")
+        return grad4[..., :3], None, None, None, None
+
+
 class _TetEnergies(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pos, tet32, inv_v, flags):
@@ -71,11 +149,21 @@ class _TetEnergies(torch.autograd.Function):
         return grad4[..., :3], None, None, None
 
 
-def tet_energies(pos, tet32, inv_v, flags=ALL):
-    """-> (amips (B,), edge (B,), volume_variance (B,)) for vertex positions (B,V,3)."""
+def tet_energies(pos, tet32, inv_v, flags=ALL, tiles=None):
+    """-> (amips (B,), edge (B,), volume_variance (B,)) for vertex positions (B,V,3).
+
+    ``tiles``: the TetTiles of ``tet32`` (built once, e.g. by GeometryEngine); looked up in / added to a small cache when
+    omitted.  An int64 ``tet32`` is converted on every call and therefore never hits the cache: pass int32."""
     if tet32.dtype != torch.int32:
         tet32 = tet32.to(torch.int32)
-    return _TetEnergies.apply(pos, tet32.contiguous(), None if inv_v is None else _f32c(inv_v), int(flags))
+    _lib.require_cuda(pos, tet32)
+    tet32 = tet32.contiguous()
+    inv = None if inv_v is None else _f32c(inv_v)
+    if _use_direct():
+        return _TetEnergies.apply(pos, tet32, inv, int(flags))
+    if tiles is None:
+        tiles = tiles_for(tet32, pos.shape[1])
+    return _TetEnergiesTiled.apply(pos, tet32, inv, int(flags), tiles)
 
 
 class _SoupEnergies(torch.autograd.Function):

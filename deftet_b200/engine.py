@@ -25,6 +25,7 @@ class GeometryEngine:
         self.n_vert = self.init_pos.shape[0]
         self.n_tet = self.tet.shape[0]
         self.inverse_v = energies.tet_inverse_v(self.init_pos, self.tet)                       # train_multigpu.py:105-110
+        self.tet_tiles = energies.TetTiles(self.tet, self.n_vert)                               # tile-local topology for the energy kernels
         f3, ft2, fs2, bnd = builders.tet_to_face(self.n_vert, self.tet)                         # train_multigpu.py:77-82
         self.tet_face_fx3, self.tet_face_tetidx_fx2, self.tet_face_slot_fx2, self.cube_boundary = f3, ft2, fs2, bnd
         self.face_table = surface.FaceTable(f3, ft2)
@@ -71,7 +72,7 @@ class GeometryEngine:
 
         if "energies" in want:
             with fork(s_en):
-                out["amips"], out["edge"], out["volume_variance"] = energies.tet_energies(pos, self.tet, self.inverse_v)
+                out["amips"], out["edge"], out["volume_variance"] = energies.tet_energies(pos, self.tet, self.inverse_v, tiles=self.tet_tiles)
                 publish(out["amips"], out["edge"], out["volume_variance"])
         if "occupancy" in want and query_points is not None:
             with fork(s_pit):

@@ -176,6 +176,47 @@ def get_boundary_index(tet_face_fx3, tet_idx_fx2, occ_bxn):
     return [faces[b, :n[b]].long() for b in range(len(n))]
 
 
+def sample_and_match(pos, faces, counts, u, v, gt, grid_res=0):
+    """The index-valued half of the chamfer op, exposed for inspection: -> q (B,Fmax*S,3) sampled surface points and
+    nn (B,Fmax*S) int32 index of the nearest gt point of each (only the first S*counts[b] entries of a sample are defined)."""
+    pos, gt, u, v = _f32c(pos.detach()), _f32c(gt), _f32c(u), _f32c(v)
+    B, V, _ = pos.shape
+    Fmax, S, M = faces.shape[1], u.shape[2], gt.shape[1]
+    dev = pos.device
+    L = _lib.lib()
+    q = torch.zeros(B, Fmax * S, 3, device=dev)
+    nn = torch.zeros(B, Fmax * S, device=dev, dtype=torch.int32)
+    wsz = L.dtb_nearest_neighbor_workspace(B, Fmax * S, M, grid_res)
+    ws = _ws(wsz, dev)
+    st = _lib.stream_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(L.dtb_surface_sample(_lib.ptr(pos), _lib.ptr(faces), _lib.ptr(counts), _lib.ptr(u), _lib.ptr(v), B, V, Fmax, S,
+                                        _lib.ptr(q), st), "dtb_surface_sample")
+        _lib.check(L.dtb_nearest_neighbor_ragged(_lib.ptr(q), _lib.ptr(counts), S, _lib.ptr(gt), _lib.ptr(nn), B, Fmax * S, M,
+                                                 grid_res, _lib.ptr(ws), wsz, st), "dtb_nearest_neighbor_ragged")
+    return q, nn
+
+
+def closest_faces(pos, faces, counts, gt, grid_res=0):
+    """The index-valued half of the surface-distance op: -> soup (B,Fmax,3,3), squared distance (B,S), closest face id (B,S) f32."""
+    pos, gt = _f32c(pos.detach()), _f32c(gt)
+    B, V, _ = pos.shape
+    Fmax, S = faces.shape[1], gt.shape[1]
+    dev = pos.device
+    L = _lib.lib()
+    soup = torch.zeros(B, Fmax, 3, 3, device=dev)
+    cd = torch.empty(B, S, device=dev)
+    cf = torch.empty(B, S, device=dev)
+    wsz = L.dtb_point_face_distance_workspace(B, S, Fmax, grid_res)
+    ws = _ws(wsz, dev)
+    st = _lib.stream_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(L.dtb_face_soup(_lib.ptr(pos), _lib.ptr(faces), _lib.ptr(counts), B, V, Fmax, _lib.ptr(soup), st), "dtb_face_soup")
+        _lib.check(L.dtb_point_face_distance_forward(_lib.ptr(gt), _lib.ptr(soup), _lib.ptr(counts), B, S, Fmax, grid_res,
+                                                     _lib.ptr(cd), _lib.ptr(cf), _lib.ptr(ws), wsz, st), "dtb_point_face_distance_forward")
+    return soup, cd, cf
+
+
 class _SurfaceChamfer(torch.autograd.Function):
     """pos (B,V,3) -> chamfer (B,): sample S points per boundary face, 1-NN into gt (B,M,3), mean distance."""
 

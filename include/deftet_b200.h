@@ -72,6 +72,21 @@ int dtb_tet_energies_backward_soup(const float* tet_bxfx4x3, const float* inv_v,
                                    const double* stats, const float* g_amips, const float* g_edge,
                                    const float* g_volvar, float* grad_soup, void* stream);
 int dtb_tet_inverse_v(const float* pos0, const int32_t* tet, int V, int T, float* inv_v, void* stream);
+/* Tile-local form of the same energies (csrc/energies_tiled.cu): the topology is re-encoded once per grid into tiles of 256
+ * consecutive tets (distinct vertex ids, 2-byte local corner ids, per-vertex incidence lists), then forward / backward stage
+ * each tile's vertices in shared memory, reduce per-sample sums without a second pass over the volumes, and scatter ONE vector
+ * reduction per (vertex, tile, sample).  Same inputs, outputs, stats layout and tolerances as dtb_tet_energies_forward /
+ * _backward_v4 (layers/DefTet/deftet.py:239-338 + autograd).
+ *   tiles      256-byte aligned device buffer of dtb_tet_tiles_bytes(T) bytes, filled by dtb_tet_tiles_build
+ *   nloc_max   device int written by the builder: the largest number of distinct vertices of any tile; the caller reads it
+ *              back once (set-up time) and passes it to the forward / backward calls                                        */
+size_t dtb_tet_tiles_bytes(int T);
+int dtb_tet_tiles_build(const int32_t* tet, int T, int V, void* tiles, size_t tiles_bytes, int32_t* nloc_max, void* stream);
+int dtb_tet_energies_forward_tiled(const float* pos, const int32_t* tet, const float* inv_v, const void* tiles, int nloc_max, int B,
+                                   int V, int T, int flags, float* amips, float* edge, float* volvar, double* stats, void* stream);
+int dtb_tet_energies_backward_tiled(const float* pos, const float* inv_v, const void* tiles, int nloc_max, int B, int V, int T,
+                                    int flags, const double* stats, const float* g_amips, const float* g_edge,
+                                    const float* g_volvar, float* grad_pos4, void* stream);
 
 /* ---- A1: point-in-tet occupancy query + barycentric weights ------------------------------------------
  * Replaces check_condition_cuda_tet_base.forward(tet_bxfx4x3, point_pos_bxnx3, condition_bxnx1, bbox_filter_bxfx6)

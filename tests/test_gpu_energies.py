@@ -68,3 +68,74 @@ def test_energies_soup_dropin(which):
     tol = 2e-5 if which == "volume" else RTOL
     assert rel_err(out, ref.detach()) < tol
     assert rel_err(dsoup.grad, soup.grad) < tol
+
+
+def _both_paths(monkeypatch, fn):
+    """Run fn() through the tile-local kernels (default) and through the direct-gather kernels of round 1."""
+    monkeypatch.delenv("DTB_ENERGY_PATH", raising=False)
+    tiled = fn()
+    monkeypatch.setenv("DTB_ENERGY_PATH", "direct")
+    direct = fn()
+    monkeypatch.delenv("DTB_ENERGY_PATH", raising=False)
+    return tiled, direct
+
+
+@pytest.mark.parametrize("res,B,group", [(12, 5, "1"), (12, 5, "2"), (12, 5, "4"), (20, 3, "8"), (16, 9, None)])
+def test_tiled_energies_match_oracle_and_direct_kernels(res, B, group, monkeypatch):
+    """energies_tiled.cu: ragged last tile, batch not a multiple of the samples-per-CTA group, every group size."""
+    from deftet_b200 import energies as E
+    if group is not None:
+        monkeypatch.setenv("DTB_ENERGY_GROUP", group)
+    g, pos, tet = deformed_grid(res, B, seed=7 * res + B)
+    inv_ref = orc.tet_inverse_v(torch.from_numpy(g.centred()), tet)
+    w = (0.7, 1.3, 1e9)
+    ref = orc.energies_with_grad(pos, tet, inv_ref, w)
+    dtet = tet.cuda().to(torch.int32)
+    inv = E.tet_inverse_v(torch.from_numpy(g.centred()).cuda(), dtet)
+
+    def run():
+        p = pos.cuda().requires_grad_(True)
+        am, ed, vv = E.tet_energies(p, dtet, inv)
+        (w[0] * am + w[1] * ed + w[2] * vv).sum().backward()
+        return am.detach(), ed.detach(), vv.detach(), p.grad
+
+    tiled, direct = _both_paths(monkeypatch, run)
+    for out in (tiled, direct):
+        assert rel_err(out[0], ref["amips"]) < RTOL and rel_err(out[1], ref["edge"]) < RTOL
+        assert rel_err(out[2], ref["volvar"]) < 2e-5
+        assert rel_err(out[3], ref["grad"]) < RTOL
+    assert rel_err(tiled[3], direct[3]) < RTOL
+
+
+def test_tiled_energies_shuffled_topology_and_flag_subsets(monkeypatch):
+    """A tet order without any locality (every tile touches ~4x256 distinct vertices -> the staging buffers grow to their
+    worst-case size) and each energy on its own (NULL gradients for the others)."""
+    from deftet_b200 import energies as E
+    g, pos, tet = deformed_grid(16, 2, seed=3)
+    perm = torch.randperm(tet.shape[0], generator=torch.Generator().manual_seed(1))
+    tet = tet[perm].contiguous()
+    inv_ref = orc.tet_inverse_v(torch.from_numpy(g.centred()), tet)
+    dtet = tet.cuda().to(torch.int32)
+    inv = E.tet_inverse_v(torch.from_numpy(g.centred()).cuda(), dtet)
+    tiles = E.TetTiles(dtet, g.n_vert)
+    assert 256 < tiles.nloc_max <= 1024
+    soup = orc.gather_tets(pos, tet)
+    for flag, fn, k in ((E.AMIPS, lambda s: orc.amips_energy(s, inv_ref), 0), (E.EDGE, orc.edge_length, 1),
+                        (E.VOLUME, lambda s: orc.volume_variance(s) * 1e9, 2)):
+        rp = pos.clone().requires_grad_(True)
+        ref = fn(orc.gather_tets(rp, tet))
+        ref.sum().backward()
+        p = pos.cuda().requires_grad_(True)
+        out = E.tet_energies(p, dtet, inv if flag == E.AMIPS else None, flags=flag, tiles=tiles)[k]
+        if flag == E.VOLUME:
+            out = out * 1e9
+        out.sum().backward()
+        tol = 2e-5 if flag == E.VOLUME else RTOL
+        assert rel_err(out, ref.detach()) < tol
+        assert rel_err(p.grad, rp.grad) < tol
+    # an inverse-matrix tensor that is not 16-byte aligned takes the plain-load staging path
+    inv_off = torch.empty(inv.numel() + 1, device="cuda")[1:].view_as(inv).copy_(inv)
+    assert inv_off.data_ptr() % 16 != 0
+    a1 = E.tet_energies(pos.cuda(), dtet, inv, tiles=tiles)[0]
+    a2 = E.tet_energies(pos.cuda(), dtet, inv_off, tiles=tiles)[0]
+    assert torch.equal(a1, a2)

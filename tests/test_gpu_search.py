@@ -153,3 +153,30 @@ def test_located_mse():
     ref = (((rx - t.double()) ** 2) * m).sum(-1) / m.sum(-1).clamp(min=1.0)
     (ref * torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)).sum().backward()
     assert rel_err(loss, ref.detach()) < 1e-6 and rel_err(dx.grad, rx.grad) < 1e-6
+
+
+@pytest.mark.parametrize("kernel", ["brick", "thread"])
+def test_nearest_neighbor_both_kernels_surface_workload(kernel, monkeypatch):
+    """The warp-cooperative brick kernel (default) and the per-thread walk of round 1 (DTB_NN_KERNEL=thread) on the shape of the
+    chamfer workload: queries within a fraction of a cell of a densely sampled surface, plus queries far from it (per-lane
+    fallback), duplicates and an empty-home-cell band."""
+    from deftet_b200 import search
+    if kernel == "thread":
+        monkeypatch.setenv("DTB_NN_KERNEL", "thread")
+    else:
+        monkeypatch.delenv("DTB_NN_KERNEL", raising=False)
+    gen = torch.Generator().manual_seed(11)
+    B, M, Q = 2, 20000, 12000
+    d = torch.randn(B, M, 3, generator=gen)
+    pts = d / d.norm(dim=-1, keepdim=True) * torch.tensor([0.3, 0.22]).reshape(B, 1, 1)
+    pts[:, 100:110] = pts[:, 0:10]
+    dq = torch.randn(B, Q, 3, generator=gen)
+    q = dq / dq.norm(dim=-1, keepdim=True) * torch.tensor([0.3, 0.22]).reshape(B, 1, 1)
+    q[:, : Q // 2] += 0.004 * torch.randn(B, Q // 2, 3, generator=gen)            # near the surface
+    q[:, Q // 2: 3 * Q // 4] *= 1.15                                               # a shell a few cells away
+    q[:, 3 * Q // 4:] = (torch.rand(B, Q - 3 * Q // 4, 3, generator=gen) - 0.5) * 2   # anywhere, also outside the bbox
+    q[:, :10] = pts[:, :10]
+    ref = orc.nearest_neighbor(q.numpy(), pts.numpy())
+    for G in (0, 16, 48, 96):
+        out = search.nearest_neighbor_index(q.cuda(), pts.cuda(), grid_res=G)
+        assert np.array_equal(out.cpu().numpy().astype(np.int64), ref), "kernel %s G=%d" % (kernel, G)
