@@ -29,6 +29,7 @@ import numpy as np
 import torch
 
 from deftet_b200 import search
+from deftet_b200.synthetic import analytic_scene
 
 
 PG_TIMEOUT_S = 120      # process-group timeout: a collective mismatch aborts quickly
@@ -36,29 +37,6 @@ LOAD_STEPS = 400        # fixed number of untimed load steps before the timed re
 
 
 # ------------------------------------------------------------------------------------------------- scene
-def analytic_scene(grid, B, P, S, seed, device):
-    """Synthetic stand-in for one ShapeNet batch: per-sample vertex deformation, GT shape = sphere,
-    occupancy labels by the analytic inside test on tet centroids, GT surface points, SDF query points."""
-    g = torch.Generator().manual_seed(seed)
-    base = torch.from_numpy(grid.centred())
-    mask = torch.from_numpy(grid.mask.astype(np.float32))
-    res = grid.res
-    deform = (torch.rand(B, grid.n_vert, 3, generator=g) * 2 - 1) * (0.25 / res) * mask
-    pos = base.unsqueeze(0) + deform
-    centres = (torch.rand(B, 1, 3, generator=g) - 0.5) * 0.1
-    radii = 0.2 + 0.15 * torch.rand(B, 1, generator=g)
-    tet = torch.from_numpy(grid.tets)
-    cen = pos[:, tet.reshape(-1)].reshape(B, -1, 4, 3).mean(dim=2)
-    occ = ((cen - centres).norm(dim=-1) < radii).float()
-    d = torch.randn(B, S, 3, generator=g)
-    gt = d / d.norm(dim=-1, keepdim=True) * radii.unsqueeze(-1) + centres
-    pts = (torch.rand(B, P, 3, generator=g) - 0.5) * 1.05                       # dataloader.py:108
-    target = ((pts - centres).norm(dim=-1) < radii).float()
-    vfield = ((pos - centres).norm(dim=-1) < radii).float()                      # per-vertex occupancy to interpolate
-    out = dict(pos=pos, occ=occ, gt=gt, pts=pts, target=target, vfield=vfield)
-    return {k: v.float().contiguous().to(device) for k, v in out.items()}
-
-
 class Step:
     """One forward+backward of the geometry losses; gradient lands in delta.grad (V,3)."""
 

@@ -299,6 +299,55 @@ __device__ __forceinline__ void nn_scan_range(unsigned j0, unsigned j1, const fl
     for (; j < j1; ++j) v.item(__ldg(sorted + j));
 }
 
+// phase 2 + fallback of the cooperative kernels (see nn_query_brick_kernel): all 32 lanes call it together.
+// Every lane searches the ball of radius rs = min(its current ball, RCAP cells); a lane that has found nothing yet searches the
+// full RCAP ball.  A cell is skipped for a lane only if it lies outside that ball or cannot beat the lane's running minimum; a
+// lane is COMPLETE when its final ball fits inside RCAP cells (then every cell that could hold the minimum was inside the region
+// and was not skipped); the others finish with the per-thread brick_walk.
+// Cells already scanned in phase 1 are skipped: either the local range `home_done` of brick (hbx,hby,hbz), or (by_ballot) every
+// cell that is the home cell `hc` of some lane.
+__device__ __forceinline__ void nn_coop_finish(float qx, float qy, float qz, bool active, NnVisitor& v, const GridParams& g, int G, float shrink,
+                                               size_t cell_base, const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
+                                               const float4* __restrict__ sorted, const unsigned long long* __restrict__ mask, bool by_ballot,
+                                               unsigned hc, int hbx, int hby, int hbz, unsigned long long home_done) {
+    const int NB = G >> 2;
+    const float rcap = NN_COOP_RCAP * g.h;
+    const float rcap2 = rcap * rcap;
+    float rs = rcap;
+    if (v.best < 1e20f) rs = fminf(sqrtf(v.best) * 1.0001f + shrink + 0.01f * g.h, rcap);
+    const int x0 = max((int)floorf((qx - rs - g.ox) * g.inv_h), 0), x1 = min((int)floorf((qx + rs - g.ox) * g.inv_h), G - 1);
+    const int y0 = max((int)floorf((qy - rs - g.oy) * g.inv_h), 0), y1 = min((int)floorf((qy + rs - g.oy) * g.inv_h), G - 1);
+    const int z0 = max((int)floorf((qz - rs - g.oz) * g.inv_h), 0), z1 = min((int)floorf((qz + rs - g.oz) * g.inv_h), G - 1);
+    const int X0 = __reduce_min_sync(0xffffffffu, x0), X1 = __reduce_max_sync(0xffffffffu, x1);
+    const int Y0 = __reduce_min_sync(0xffffffffu, y0), Y1 = __reduce_max_sync(0xffffffffu, y1);
+    const int Z0 = __reduce_min_sync(0xffffffffu, z0), Z1 = __reduce_max_sync(0xffffffffu, z1);
+    for (int bz = Z0 >> 2; bz <= (Z1 >> 2); ++bz)
+        for (int by = Y0 >> 2; by <= (Y1 >> 2); ++by)
+            for (int bx = X0 >> 2; bx <= (X1 >> 2); ++bx) {
+                const size_t bk = ((size_t)bz * NB + by) * NB + bx;
+                unsigned long long m = __ldg(mask + (cell_base >> 6) + bk);
+                if (!by_ballot && bx == hbx && by == hby && bz == hbz) m &= ~home_done;
+                if (!m) continue;
+                // cells of this brick inside the region
+                m &= brick_xmask(max(X0 - 4 * bx, 0), min(X1 - 4 * bx, 3)) & brick_ymask(max(Y0 - 4 * by, 0), min(Y1 - 4 * by, 3)) &
+                     brick_zmask(max(Z0 - 4 * bz, 0), min(Z1 - 4 * bz, 3));
+                const float lx = g.ox + (float)(4 * bx) * g.h, ly = g.oy + (float)(4 * by) * g.h, lz = g.oz + (float)(4 * bz) * g.h;
+                const size_t cb = cell_base + bk * 64;
+                while (m) {
+                    const int k = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    if (by_ballot && __any_sync(0xffffffffu, hc == (unsigned)(bk * 64 + k))) continue;      // scanned in phase 1
+                    const float cxl = lx + (float)(k & 3) * g.h, cyl = ly + (float)((k >> 2) & 3) * g.h, czl = lz + (float)(k >> 4) * g.h;
+                    const bool need = !(box_dist2(qx, qy, qz, cxl, cyl, czl, g.h, shrink) > fminf(v.best, rcap2));
+                    if (!__any_sync(0xffffffffu, need)) continue;
+                    nn_scan_range(__ldg(cell_start + cb + k), __ldg(cell_end + cb + k), sorted, v);
+                }
+            }
+    const bool complete = (v.best < 1e20f) && (sqrtf(v.best) * 1.0001f + shrink + 0.01f * g.h <= rcap);
+    if (active && !complete)
+        brick_walk(qx, qy, qz, g, G, 0.0f, cell_start, cell_end, sorted, mask, cell_base, v);
+}
+
 __global__ void __launch_bounds__(128) nn_query_brick_kernel(int Q, int G, const unsigned* __restrict__ bbox_ord,
                                                              const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
                                                              const float4* __restrict__ sorted, const unsigned long long* __restrict__ mask,
@@ -326,51 +375,45 @@ __global__ void __launch_bounds__(128) nn_query_brick_kernel(int Q, int G, const
         // ---- phase 1: the chunk's home cells (sorted order => contiguous local ids) -----------------------------------------
         const int hmin = __reduce_min_sync(0xffffffffu, hloc), hmax = __reduce_max_sync(0xffffffffu, hloc);
         nn_scan_range(__ldg(cell_start + c0 + hmin), __ldg(cell_end + c0 + hmax), sorted, v);
-        // ---- phase 2: the cells the lanes' search balls reach -------------------------------------------------------------------
-        // Every lane searches the ball of radius rs = min(its current ball, RCAP cells); a lane that has found nothing yet
-        // searches the full RCAP ball.  A cell is skipped for a lane only if it lies outside that ball or cannot beat the
-        // lane's running minimum; the lane is COMPLETE when its final ball fits inside RCAP cells (then every cell that could
-        // hold the minimum was inside the region and was not skipped).
-        const float rcap = NN_COOP_RCAP * g.h;
-        const float rcap2 = rcap * rcap;
-        float rs = rcap;
-        if (v.best < 1e20f) rs = fminf(sqrtf(v.best) * 1.0001f + shrink + 0.01f * g.h, rcap);
-        const int x0 = max((int)floorf((q.x - rs - g.ox) * g.inv_h), 0), x1 = min((int)floorf((q.x + rs - g.ox) * g.inv_h), G - 1);
-        const int y0 = max((int)floorf((q.y - rs - g.oy) * g.inv_h), 0), y1 = min((int)floorf((q.y + rs - g.oy) * g.inv_h), G - 1);
-        const int z0 = max((int)floorf((q.z - rs - g.oz) * g.inv_h), 0), z1 = min((int)floorf((q.z + rs - g.oz) * g.inv_h), G - 1);
-        const int X0 = __reduce_min_sync(0xffffffffu, x0), X1 = __reduce_max_sync(0xffffffffu, x1);
-        const int Y0 = __reduce_min_sync(0xffffffffu, y0), Y1 = __reduce_max_sync(0xffffffffu, y1);
-        const int Z0 = __reduce_min_sync(0xffffffffu, z0), Z1 = __reduce_max_sync(0xffffffffu, z1);
-        {
-            const unsigned long long home_done = (hmax >= 63 ? ~0ull : ((1ull << (hmax + 1)) - 1ull)) & ~((1ull << hmin) - 1ull);
-            for (int bz = Z0 >> 2; bz <= (Z1 >> 2); ++bz)
-                for (int by = Y0 >> 2; by <= (Y1 >> 2); ++by)
-                    for (int bx = X0 >> 2; bx <= (X1 >> 2); ++bx) {
-                        const size_t bk = ((size_t)bz * NB + by) * NB + bx;
-                        unsigned long long m = __ldg(mask + (cell_base >> 6) + bk);
-                        if (bx == bx0 && by == by0 && bz == bz0) m &= ~home_done;
-                        if (!m) continue;
-                        // cells of this brick inside the region
-                        m &= brick_xmask(max(X0 - 4 * bx, 0), min(X1 - 4 * bx, 3)) & brick_ymask(max(Y0 - 4 * by, 0), min(Y1 - 4 * by, 3)) &
-                             brick_zmask(max(Z0 - 4 * bz, 0), min(Z1 - 4 * bz, 3));
-                        const float lx = g.ox + (float)(4 * bx) * g.h, ly = g.oy + (float)(4 * by) * g.h, lz = g.oz + (float)(4 * bz) * g.h;
-                        const size_t cb = cell_base + bk * 64;
-                        while (m) {
-                            const int k = __ffsll((long long)m) - 1;
-                            m &= m - 1;
-                            const float cxl = lx + (float)(k & 3) * g.h, cyl = ly + (float)((k >> 2) & 3) * g.h, czl = lz + (float)(k >> 4) * g.h;
-                            const bool need = !(box_dist2(q.x, q.y, q.z, cxl, cyl, czl, g.h, shrink) > fminf(v.best, rcap2));
-                            if (!__any_sync(0xffffffffu, need)) continue;
-                            nn_scan_range(__ldg(cell_start + cb + k), __ldg(cell_end + cb + k), sorted, v);
-                        }
-                    }
-        }
-        // ---- fallback: the per-thread walk for the lanes whose final ball does not fit into the searched region -----------------
-        const bool complete = (v.best < 1e20f) && (sqrtf(v.best) * 1.0001f + shrink + 0.01f * g.h <= rcap);
-        if (active && !complete)
-            brick_walk(q.x, q.y, q.z, g, G, 0.0f, cell_start, cell_end, sorted, mask, cell_base, v);
+        const unsigned long long home_done = (hmax >= 63 ? ~0ull : ((1ull << (hmax + 1)) - 1ull)) & ~((1ull << hmin) - 1ull);
+        nn_coop_finish(q.x, q.y, q.z, active, v, g, G, shrink, cell_base, cell_start, cell_end, sorted, mask, false, 0u, bx0, by0, bz0, home_done);
         if (active) result[(size_t)b * Q + __float_as_int(q.w)] = v.bi;
     }
+}
+
+// ---- grouped queries (the chamfer workload): the queries arrive in groups of `q_mult` consecutive points sampled on ONE
+// boundary face (dtb_surface_sample), i.e. each group is already a spatially compact patch a fraction of a grid cell wide.
+// One warp takes (a chunk of up to 32 queries of) one group in its ORIGINAL order -- no query binning pass at all -- and
+// proceeds like the brick kernel: phase 1 scans the distinct home cells of its lanes, phase 2 the remaining cells any lane's
+// ball reaches.  Because the patch is compact the union of candidates over the warp is close to what a single lane needs.
+__global__ void __launch_bounds__(128) nn_query_group_kernel(const float* __restrict__ queries, int Q, const int32_t* __restrict__ q_counts, int q_mult,
+                                                             int G, const unsigned* __restrict__ bbox_ord, const unsigned* __restrict__ cell_start,
+                                                             const unsigned* __restrict__ cell_end, const float4* __restrict__ sorted,
+                                                             const unsigned long long* __restrict__ mask, int* __restrict__ result) {
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int cpg = (q_mult + 31) >> 5;                       // chunks per group
+    const int group = w / cpg, chunk = w - group * cpg;
+    if (group >= q_counts[b]) return;                         // warp-uniform
+    const int l0 = chunk * 32;
+    const bool active = l0 + lane < q_mult;
+    const size_t qi = (size_t)b * Q + (size_t)group * q_mult + (active ? l0 + lane : l0);      // idle lanes copy the chunk's first query
+    const float qx = __ldg(queries + qi * 3), qy = __ldg(queries + qi * 3 + 1), qz = __ldg(queries + qi * 3 + 2);
+    const size_t cell_base = (size_t)b * G * G * G;
+    const GridParams g = grid_params(bbox_ord, b, G);
+    const float shrink = 1e-3f * g.h + 1e-6f * (fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz) + (float)G * g.h);   // as brick_walk (inflate = 0)
+    NnVisitor v{qx, qy, qz, 1e20f, 0};
+    const unsigned hc = cell_index(cell_coord(qx, g.ox, g.inv_h, G), cell_coord(qy, g.oy, g.inv_h, G), cell_coord(qz, g.oz, g.inv_h, G), G, true);
+    // ---- phase 1: the distinct home cells of the lanes, every lane evaluates every candidate ------------------------------------
+    unsigned todo = 0xffffffffu;
+    while (todo) {
+        const unsigned c = __shfl_sync(0xffffffffu, hc, __ffs(todo) - 1);
+        nn_scan_range(__ldg(cell_start + cell_base + c), __ldg(cell_end + cell_base + c), sorted, v);
+        todo &= ~__ballot_sync(0xffffffffu, hc == c);
+    }
+    nn_coop_finish(qx, qy, qz, active, v, g, G, shrink, cell_base, cell_start, cell_end, sorted, mask, true, hc, 0, 0, 0, 0ull);
+    if (active) result[qi] = v.bi;
 }
 
 // ---- interpolation of a per-vertex field at the query points through the barycentric weights ----------
@@ -557,6 +600,10 @@ static bool nn_use_thread_walk() {
     const char* e = getenv("DTB_NN_KERNEL");          // read per call: tests and A/B runs toggle it inside one process
     return e && e[0] == 't';
 }
+static bool nn_use_brick_for_groups() {
+    const char* e = getenv("DTB_NN_KERNEL");          // "brick": sort the grouped queries by cell like ungrouped ones (A/B)
+    return e && e[0] == 'b';
+}
 static int nearest_neighbor_impl(const float* queries, const float* points, int32_t* result, int B, int Q, int M, int G,
                                  const int32_t* q_counts, int q_mult, void* workspace, size_t workspace_bytes, void* stream) {
     DTB_REQUIRE(B > 0 && Q >= 0 && M >= 0, "nearest_neighbor: bad sizes");
@@ -582,6 +629,17 @@ static int nearest_neighbor_impl(const float* queries, const float* points, int3
     if (!ws.ok || !workspace) { set_error("nearest_neighbor: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return DTB_EWORKSPACE; }
     int rc = pointgrid_build(pg, points, false, st);
     if (rc) return rc;
+    if (q_counts && q_mult > 0 && !nn_use_thread_walk() && !nn_use_brick_for_groups()) {
+        // grouped queries: no query binning, one warp per (chunk of a) group in the original order
+        const int cpg = (q_mult + 31) / 32;
+        const long long warps = (long long)(Q / q_mult) * cpg;
+        dim3 grid(cdiv(warps, 4), B);
+        prof_begin(PROF_NN_QUERY, st);
+        nn_query_group_kernel<<<grid, 128, 0, st>>>(queries, Q, q_counts, q_mult, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask, result);
+        DTB_LAUNCH_CHECK("nn_query_group");
+        prof_end(PROF_NN_QUERY, st);
+        return DTB_OK;
+    }
     dim3 gq(cdiv(Q, 256), B);
     DTB_CUDA(cudaMemsetAsync(qstart, 0, cells * sizeof(unsigned), st));
     nn_qbin_count_kernel<<<gq, 256, 0, st>>>(queries, Q, G, pg.bbox_ord, q_counts, q_mult, qstart, qcell);

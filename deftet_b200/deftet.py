@@ -12,6 +12,70 @@ from . import energies, render, search, surface
 EPS = 1e-10
 
 
+class _LazyFaceList:
+    """The per-sample list of boundary-face index tensors (``get_boundary_index`` return value) backed by the padded-ragged
+    device buffers: nothing is read back to the host until a caller actually indexes / iterates it (the training path of
+    parallel.py:199-214 never does, only inference with return_surf=True)."""
+
+    def __init__(self, faces, counts):
+        self._faces, self._counts, self._list = faces, counts, None
+
+    def _materialise(self):
+        if self._list is None:
+            n = self._counts.tolist()
+            self._list = [self._faces[b, :n[b]].long() for b in range(len(n))]
+        return self._list
+
+    def __len__(self):
+        return int(self._faces.shape[0])
+
+    def __getitem__(self, i):
+        return self._materialise()[i]
+
+    def __iter__(self):
+        return iter(self._materialise())
+
+
+class _TopologyCache:
+    """Per-module cache of what is derived from the (stride-0 expanded, int64) topology tensors the trainer passes on every
+    call (train_multigpu.py:185-194): the int32 copy + tile-local encoding of the tet list, and the int32 face table.
+    Keyed on (storage address, shape, version, device) of the SOURCE tensor, which the entry keeps alive -- so the address
+    cannot be recycled for another topology while the entry exists.  A tensor is only given the (set-up-time) tile encoding
+    on its SECOND sighting: a transient per-call copy (what nn.DataParallel scatters to the non-primary devices) runs the
+    direct-gather kernels instead of paying a build + host synchronisation on every step."""
+
+    def __init__(self, capacity=6):
+        import threading
+        self.capacity, self.lock, self.tets, self.tables = capacity, threading.Lock(), {}, {}
+
+    @staticmethod
+    def _key(t):
+        return (t.data_ptr(), tuple(t.shape), t._version, t.device.index)
+
+    def tet(self, tet_fx4, n_vert):
+        key = self._key(tet_fx4)
+        with self.lock:
+            e = self.tets.get(key)
+            if e is None:
+                if len(self.tets) >= self.capacity:
+                    self.tets.pop(next(iter(self.tets)))
+                e = self.tets[key] = {"src": tet_fx4, "tet32": tet_fx4.to(torch.int32).contiguous(), "tiles": None, "seen": 0}
+            e["seen"] += 1
+            if e["tiles"] is None and e["seen"] >= 2 and energies._use_tiled() and not torch.cuda.is_current_stream_capturing():
+                e["tiles"] = energies.TetTiles(e["tet32"], n_vert)
+            return e["tet32"], e["tiles"]
+
+    def table(self, tet_face_fx3, tet_idx_fx2):
+        key = self._key(tet_face_fx3) + self._key(tet_idx_fx2)
+        with self.lock:
+            e = self.tables.get(key)
+            if e is None:
+                if len(self.tables) >= self.capacity:
+                    self.tables.pop(next(iter(self.tables)))
+                e = self.tables[key] = (surface.FaceTable(tet_face_fx3, tet_idx_fx2), tet_face_fx3, tet_idx_fx2)
+            return e[0]
+
+
 class DefTet(nn.Module):
     def __init__(self, device=None):
         super(DefTet, self).__init__()
@@ -20,53 +84,64 @@ class DefTet(nn.Module):
         self.features_fixed = False
         self.z_window_radius = 0.025
         self.inverse_v = None
-        self._face_table_key = None
-        self._face_table = None
+        self._topo = _TopologyCache()           # shared (by reference) with the replicas nn.DataParallel makes
+        self._inv_on = {}                       # inverse_v per device (the reference re-copies it on every call, deftet.py:83)
 
     # ---- occupancy label (deftet.py:33-49) ------------------------------------------------------------------
-    def check_tet_inside_sdfs(self, tet_bxfx4x3, mesh_list):
+    def check_tet_inside_sdfs(self, tet_bxfx4x3, mesh_list, centers=None):
         verts, faces = mesh_list[0], mesh_list[1]
         with torch.no_grad():
             occupancy = []
-            for v, f, tet_fx4x3 in zip(verts, faces, tet_bxfx4x3):
-                center = torch.mean(tet_fx4x3, dim=1)
+            for i, (v, f) in enumerate(zip(verts, faces)):
+                center = torch.mean(tet_bxfx4x3[i], dim=1) if centers is None else centers[i]
                 result = render.check_sign(v, f[0], center.unsqueeze(dim=0), hash_resolution=512)
                 occupancy.append(result.unsqueeze(-1))
             occupancy = torch.cat(occupancy, dim=0).float()
         return occupancy
 
     def _table(self, tet_face_fx3, tet_idx_fx2):
-        key = (tet_face_fx3.data_ptr(), tet_idx_fx2.data_ptr(), tet_face_fx3.shape[0])
-        if key != self._face_table_key:
-            self._face_table = surface.FaceTable(tet_face_fx3, tet_idx_fx2)
-            self._face_table_key = key
-        return self._face_table
+        return self._topo.table(tet_face_fx3, tet_idx_fx2)
+
+    def _inverse_v_on(self, device):
+        inv = self.inverse_v
+        if inv.device == device:
+            return inv
+        key = (inv.data_ptr(), inv._version, device.index)
+        hit = self._inv_on.get(device.index)
+        if hit is None or hit[0] != key:
+            hit = self._inv_on[device.index] = (key, inv.detach().to(device), inv)
+        return hit[1]
 
     # ---- deftet.py:51-130 ---------------------------------------------------------------------------------------
     def forward_surface_align(self, vertice_pos, point_pos_bxpx3, tetrahedron_bxfx4=None, mesh_list=None, gt_surface_points=None,
                               tet_face_bxfx3=None, inference=False, pred_occ=None, tet_face_tet_bx4fx2=None, save=False, save_name=None,
                               inference_threshold=0.4):
-        tetrahedron_bxfx4 = tetrahedron_bxfx4.long()
-        tet32 = tetrahedron_bxfx4[0].to(torch.int32).contiguous()       # stride-0 batch view of one grid (train_multigpu.py:185-194)
-        B = vertice_pos.shape[0]
-        tet_bxfx4x3 = torch.gather(input=vertice_pos.unsqueeze(2).expand(-1, -1, 4, -1),
-                                   index=tetrahedron_bxfx4.unsqueeze(-1).expand(-1, -1, -1, 3), dim=1) if mesh_list is not None else None
-        center_occ = self.check_tet_inside_sdfs(tet_bxfx4x3, mesh_list)
-        boundary = self.get_boundary_index(tet_face_bxfx3[0], tet_face_tet_bx4fx2[0], center_occ.squeeze(dim=-1))
-        amips_energy, edge, volume_variance = energies.tet_energies(vertice_pos, tet32, self.inverse_v.to(vertice_pos.device))
-        # batched surface stage (replaces the loop of :89-103); RNG calls in the reference's order
-        counts = [int(b.shape[0]) for b in boundary]
-        Fmax = max(max(counts), 1)
-        faces = torch.zeros(B, Fmax, 3, device=vertice_pos.device, dtype=torch.int32)
-        u = torch.zeros(B, Fmax, 20, device=vertice_pos.device)
-        v = torch.zeros(B, Fmax, 20, device=vertice_pos.device)
-        for i in range(B):
-            if counts[i]:
-                faces[i, :counts[i]] = boundary[i].to(torch.int32)
-                u[i, :counts[i]] = torch.sqrt(torch.rand(size=(1, counts[i], 20, 1), device=vertice_pos.device))[0, :, :, 0]
-                v[i, :counts[i]] = torch.rand(size=(1, counts[i], 20, 1), device=vertice_pos.device)[0, :, :, 0]
-        cnt = torch.tensor(counts, device=vertice_pos.device, dtype=torch.int32)
+        """Same arguments and return tuples as the reference method.  The per-sample Python loop of :89-103 is one batched
+        launch sequence on padded-ragged (B,Fmax,3)+counts buffers; the only host synchronisation is ONE scalar read (the
+        largest boundary-face count, which sizes those buffers) -- the reference synchronises B times per loss.  The surface
+        samples use one (u, v) pair of batched draws, u first, as mesh_utils.py:290-299 orders them."""
+        dev = vertice_pos.device
+        B, V = vertice_pos.shape[0], vertice_pos.shape[1]
+        tet32, tiles = self._topo.tet(tetrahedron_bxfx4[0], V)       # stride-0 batch view of one grid (train_multigpu.py:185-194)
+        with torch.no_grad():
+            # tet centroids without materialising the (B,T,4,3) gather of deftet.py:66-68
+            centers = vertice_pos.detach()[:, tet32.long().reshape(-1)].reshape(B, -1, 4, 3).mean(dim=2)
+        center_occ = self.check_tet_inside_sdfs(None, mesh_list, centers=centers)
+        table = self._table(tet_face_bxfx3[0], tet_face_tet_bx4fx2[0])
+        cap = table.n_face
+        faces_cap, cnt, _ = surface.boundary_faces(table, center_occ.squeeze(dim=-1), cap)
+        Fmax = max(int(cnt.max()), 1)                                # the one host read of the call
+        faces = faces_cap[:, :Fmax].contiguous()
+        boundary = _LazyFaceList(faces, cnt)
+        inv = self._inverse_v_on(dev)
+        if tiles is not None:
+            amips_energy, edge, volume_variance = energies.tet_energies(vertice_pos, tet32, inv, tiles=tiles)
+        else:
+            amips_energy, edge, volume_variance = energies.tet_energies_direct(vertice_pos, tet32, inv)
+        u = torch.sqrt(torch.rand(size=(B, Fmax, 20), device=dev))
+        v = torch.rand(size=(B, Fmax, 20), device=dev)
         gt = gt_surface_points.reshape(B, -1, 3)
+        # (a sample without boundary faces contributes the constant 1 to each surface loss, deftet.py:162-166: the kernels do that)
         sum_normal_loss = surface.surface_normal_loss(vertice_pos, faces, cnt).mean().reshape(1)
         sum_chamfer_distance = surface.surface_chamfer(vertice_pos, faces, cnt, u, v, gt).mean().reshape(1)
         sum_analytic_distance = surface.surface_distance(vertice_pos, faces, cnt, gt).mean().reshape(1)
@@ -120,8 +195,7 @@ class DefTet(nn.Module):
     def get_boundary_index(self, tet_face_fx3, tet_idx_fx2, occ_bxn):
         table = self._table(tet_face_fx3, tet_idx_fx2)
         faces, counts, _ = surface.boundary_faces(table, occ_bxn, table.n_face)
-        n = counts.tolist()
-        return [faces[b, :n[b]].long() for b in range(len(n))]
+        return _LazyFaceList(faces, counts)
 
     def get_internal_index(self, tet_face_fx3, tet_idx_fx2, occ_bxn):
         occ2 = torch.gather(input=occ_bxn, index=tet_idx_fx2.reshape(-1).unsqueeze(0).expand(occ_bxn.shape[0], -1), dim=1)

@@ -73,9 +73,12 @@ def tiles_for(tet32: torch.Tensor, n_vert: int) -> TetTiles:
     return t
 
 
-def _use_direct():
+def _use_tiled():
+    """The tile-local kernels (csrc/energies_tiled.cu) are an OPT-IN alternative: measured on B200 at res 70 b8 they execute
+    20-40 % more instructions than the direct-gather kernels for the same issue rate (profiles/r2_ab_energies.md) -- the
+    kernels are issue-bound, not load/RED-bound -- so the direct kernels stay the default."""
     import os
-    return os.environ.get("DTB_ENERGY_PATH", "") == "direct"      # round-1 direct-gather kernels (A/B measurements)
+    return os.environ.get("DTB_ENERGY_PATH", "") == "tiled"
 
 
 class _TetEnergiesTiled(torch.autograd.Function):
@@ -152,18 +155,26 @@ class _TetEnergies(torch.autograd.Function):
 def tet_energies(pos, tet32, inv_v, flags=ALL, tiles=None):
     """-> (amips (B,), edge (B,), volume_variance (B,)) for vertex positions (B,V,3).
 
-    ``tiles``: the TetTiles of ``tet32`` (built once, e.g. by GeometryEngine); looked up in / added to a small cache when
-    omitted.  An int64 ``tet32`` is converted on every call and therefore never hits the cache: pass int32."""
+    ``tiles``: the TetTiles of ``tet32`` for the opt-in tile-local kernels (DTB_ENERGY_PATH=tiled); looked up in / added to a
+    small cache when omitted."""
     if tet32.dtype != torch.int32:
         tet32 = tet32.to(torch.int32)
     _lib.require_cuda(pos, tet32)
     tet32 = tet32.contiguous()
     inv = None if inv_v is None else _f32c(inv_v)
-    if _use_direct():
+    if not _use_tiled():
         return _TetEnergies.apply(pos, tet32, inv, int(flags))
     if tiles is None:
         tiles = tiles_for(tet32, pos.shape[1])
     return _TetEnergiesTiled.apply(pos, tet32, inv, int(flags), tiles)
+
+
+def tet_energies_direct(pos, tet32, inv_v, flags=ALL):
+    """The direct-gather kernels (csrc/energies.cu): no per-topology set-up, for topologies seen only once."""
+    if tet32.dtype != torch.int32:
+        tet32 = tet32.to(torch.int32)
+    _lib.require_cuda(pos, tet32)
+    return _TetEnergies.apply(pos, tet32.contiguous(), None if inv_v is None else _f32c(inv_v), int(flags))
 
 
 class _SoupEnergies(torch.autograd.Function):

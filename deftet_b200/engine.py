@@ -25,13 +25,20 @@ class GeometryEngine:
         self.n_vert = self.init_pos.shape[0]
         self.n_tet = self.tet.shape[0]
         self.inverse_v = energies.tet_inverse_v(self.init_pos, self.tet)                       # train_multigpu.py:105-110
-        self.tet_tiles = energies.TetTiles(self.tet, self.n_vert)                               # tile-local topology for the energy kernels
+        self._tet_tiles = None
         f3, ft2, fs2, bnd = builders.tet_to_face(self.n_vert, self.tet)                         # train_multigpu.py:77-82
         self.tet_face_fx3, self.tet_face_tetidx_fx2, self.tet_face_slot_fx2, self.cube_boundary = f3, ft2, fs2, bnd
         self.face_table = surface.FaceTable(f3, ft2)
         self.max_boundary_faces = int(max_boundary_faces)
         self.samples_per_face = int(samples_per_face)
         self._streams = None
+
+    @property
+    def tet_tiles(self):
+        """Tile-local topology for the opt-in tiled energy kernels (built on first use)."""
+        if self._tet_tiles is None:
+            self._tet_tiles = energies.TetTiles(self.tet, self.n_vert)
+        return self._tet_tiles
 
     def vertex_adjacency(self, normalize=True):
         """Row-normalised vertex adjacency (train_multigpu.py:72-75) as a torch sparse tensor."""
@@ -72,7 +79,7 @@ class GeometryEngine:
 
         if "energies" in want:
             with fork(s_en):
-                out["amips"], out["edge"], out["volume_variance"] = energies.tet_energies(pos, self.tet, self.inverse_v, tiles=self.tet_tiles)
+                out["amips"], out["edge"], out["volume_variance"] = energies.tet_energies(pos, self.tet, self.inverse_v, tiles=self._tet_tiles)
                 publish(out["amips"], out["edge"], out["volume_variance"])
         if "occupancy" in want and query_points is not None:
             with fork(s_pit):

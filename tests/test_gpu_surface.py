@@ -168,3 +168,37 @@ def test_engine_concurrent_streams_equal_serial():
     assert abs(res[0][0] - res[1][0]) < 1e-5 * abs(res[0][0])
     assert torch.equal(res[0][2], res[1][2])
     assert rel_err(res[1][1], res[0][1]) < 1e-5
+
+
+@pytest.mark.parametrize("S", [20, 40, 70])
+def test_grouped_nearest_neighbour_kernels_agree_with_oracle(S, monkeypatch):
+    """The 1-NN of the sampled surface points through the three query kernels -- grouped (default for the chamfer path: one
+    warp per face's samples, no query binning), brick (queries sorted by cell) and the per-thread walk of round 1 -- must all be
+    the brute-force answer of the oracle, for group sizes below, above and far above one warp."""
+    from deftet_b200 import surface
+    g, pos, tet, occ, f3, ft2, gt = _scene(10, 2, 13)
+    table = surface.FaceTable(f3.cuda(), ft2.cuda())
+    Fmax = 700
+    faces, counts, overflow = surface.boundary_faces(table, occ.cuda(), Fmax)
+    assert int(overflow.item()) == 0
+    gen = torch.Generator().manual_seed(S)
+    u = torch.sqrt(torch.rand(2, Fmax, S, generator=gen)).cuda()
+    v = torch.rand(2, Fmax, S, generator=gen).cuda()
+    gtc = gt.cuda()
+    gtc[:, 50:60] = gtc[:, 0:10]                      # duplicated targets: the lowest index must win
+    outs = {}
+    for kern in ("group", "brick", "thread"):
+        if kern == "group":
+            monkeypatch.delenv("DTB_NN_KERNEL", raising=False)
+        else:
+            monkeypatch.setenv("DTB_NN_KERNEL", kern)
+        for G in (0, 16, 64):
+            q, nn = surface.sample_and_match(pos.cuda(), faces, counts, u, v, gtc, G)
+            outs[(kern, G)] = nn.clone()
+    monkeypatch.delenv("DTB_NN_KERNEL", raising=False)
+    cnt = counts.tolist()
+    for b in range(2):
+        n = cnt[b] * S
+        ref = orc.nearest_neighbor(q[b:b + 1, :n].cpu().numpy(), gtc[b:b + 1].cpu().numpy())
+        for key, nn in outs.items():
+            assert np.array_equal(nn[b, :n].cpu().numpy().astype(np.int64), ref[0]), key
