@@ -330,7 +330,10 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
     const float slack = 1e-3f * g.h + 1e-6f * (fabsf(g.ox) + fabsf(g.oy) + fabsf(g.oz) + (float)G * g.h);
     // only faces whose centroid lies within `reach` of this brick are staged; a query is final when its search ball
     // (sqrt(best) + rmax) stays inside that region, otherwise it falls back to the general walk
-    const float reach = rmax + PFD_REACH_H * g.h;
+    // The region can only be certified where it was staged, i.e. inside the 3x3x3 bricks: when the faces are large against the
+    // grid (rmax + 1.25 h > one brick; found by the res-40 scale parity test, where a small shape gives a fine grid) it is clamped
+    // to them, and the queries whose ball leaves the clamped region take the general walk.
+    const float reach = fminf(rmax + PFD_REACH_H * g.h, bw);
     const float lx0 = g.ox + (float)bx0 * bw, ly0 = g.oy + (float)by0 * bw, lz0 = g.oz + (float)bz0 * bw;
     const float rlo[3] = {lx0 - reach, ly0 - reach, lz0 - reach}, rhi[3] = {lx0 + bw + reach, ly0 + bw + reach, lz0 + bw + reach};
     const float gmax = (float)G * g.h;

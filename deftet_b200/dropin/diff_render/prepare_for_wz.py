@@ -66,3 +66,14 @@ def generate_subdivision(tet_list_tx4, tet_points_px3, tet_feat_pxk, tet_list_su
     sig = None if tet_list_subdiv_sig is None else _dev(np.asarray(tet_list_subdiv_sig, dtype=bool))
     p, f, t = topology.generate_subdivision(_dev(tet_list_tx4), _dev(tet_points_px3, torch.float32), _dev(tet_feat_pxk, torch.float32), sig)
     return p.cpu().numpy().astype(tet_points_px3.dtype), f.cpu().numpy().astype(tet_feat_pxk.dtype), _np64(t)
+
+
+# every other name of the reference module comes from the checkout at DEFTET_REFERENCE_ROOT (see dropin/_fallthrough.py)
+from _fallthrough import adopt_reference_module as _adopt, missing_attribute as _missing  # noqa: E402
+
+_REPLACED = ('read_tetrahedron', 'tet_to_face_idx', 'generate_point_adj_idx', 'delete_tet', 'generate_edge', 'generate_tet_edge_idx', 'generate_subdivision')
+_reference = _adopt(globals(), 'diff_render/diftet_6_subdiv/3_model/prepare_for_wz.py', _REPLACED)
+
+
+def __getattr__(name):
+    raise _missing(__name__, name)

@@ -17,3 +17,14 @@ def tet_adj_share(tet_list_tx4, n_point):
         rows = np.flatnonzero(nbr[:, i] >= 0)
         adj_list.append(coo_matrix((np.ones(rows.shape[0]), (rows, nbr[rows, i])), shape=(n_tet, n_tet)))
     return adj_list, nbr
+
+
+# every other name of the reference module comes from the checkout at DEFTET_REFERENCE_ROOT (see dropin/_fallthrough.py)
+from _fallthrough import adopt_reference_module as _adopt, missing_attribute as _missing  # noqa: E402
+
+_REPLACED = ('tet_adj_share',)
+_reference = _adopt(globals(), 'diff_render/diftet_6_subdiv/3_model/utils_tetsv.py', _REPLACED)
+
+
+def __getattr__(name):
+    raise _missing(__name__, name)

@@ -85,3 +85,24 @@ def analytic_scene(grid, B, P, S, seed, device, shapes=(1, 3), info=None):
     if info is not None:
         info["n_shapes"] = n_shapes
     return out
+
+
+def icosphere(level=4):
+    """Unit icosphere: (V,3) float32 vertices, (F,3) int64 faces (outward winding), 20 * 4**level faces -- a watertight GT mesh
+    for the paths that label occupancy with check_sign (DefTet.check_tet_inside_sdfs, layers/DefTet/deftet.py:33-49)."""
+    t = (1.0 + 5 ** 0.5) / 2
+    v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t], [t, 0, -1], [t, 0, 1],
+                  [-t, 0, -1], [-t, 0, 1]], dtype=np.float64)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    f = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2], [10, 7, 6], [7, 1, 8],
+                  [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5], [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]], dtype=np.int64)
+    for _ in range(level):
+        e = np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]), axis=1)            # 3F edges, (ab, bc, ca) blocks
+        uniq, inv = np.unique(e, axis=0, return_inverse=True)
+        mid = v[uniq[:, 0]] + v[uniq[:, 1]]
+        mid /= np.linalg.norm(mid, axis=1, keepdims=True)
+        m = inv.reshape(3, -1) + v.shape[0]
+        ab, bc, ca = m[0], m[1], m[2]
+        v = np.concatenate([v, mid])
+        f = np.concatenate([np.stack([f[:, 0], ab, ca], 1), np.stack([f[:, 1], bc, ab], 1), np.stack([f[:, 2], ca, bc], 1), np.stack([ab, bc, ca], 1)])
+    return v.astype(np.float32), f

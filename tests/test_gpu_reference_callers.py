@@ -8,10 +8,10 @@ unpacks it into a temporary directory, puts deftet_b200/dropin FIRST on PYTHONPA
       train_multigpu.py:236-273 with a stub network, two optimiser steps; losses and the gradient of step 1 must equal the CPU
       oracle pipeline (<= 1e-5 relative for the RNG-free terms, see the harness).  Importing train_multigpu.py and eval.py under
       the drop-in is part of it (utils.mesh_utils.save_mesh, tet_utils.c_tet_adj_share).
-  (b) tests/x1/harness_diffrender.py          three iterations of optimzie() of
-      diff_render/diftet_6_subdiv/6_optim/optim_with_mask_subdiv_from_gridmov.py:173-286 on a res-8 grid, once with the
-      reference's own Deftet model + rendermeshcolor over the drop-in leaf modules and the Kaolin shim, once with the fused
-      drop-in model.
+  (b) `python -m deftet_b200.run [--leaf] optim_with_mask_subdiv_from_gridmov.py ...` -- the reference's diff_render script
+      itself (diff_render/diftet_6_subdiv/6_optim, __main__ block included), three iterations per stage on a res-8 grid and a
+      synthetic on-disk data set, once with the reference's own Deftet model + rendermeshcolor over the drop-in leaf modules
+      and the Kaolin shim, once with the fused drop-in model.
   (c) harness_parallel.py 2 devices           the same wrapper under nn.DataParallel on two GPUs (train_multigpu.py:136-140);
       skipped unless two devices are visible (run under `gpurun --gpus 2`).
 """
@@ -65,17 +65,65 @@ def test_reference_parallel_wrapper_two_train_steps(reference_copy, tmp_path):
     for k in ("surf", "area", "normal", "edge", "amips", "lap", "delta", "occ", "surf_chamfer"):
         tol = 2e-5 if k == "area" else 1e-5
         assert rec["loss_rel_err"][k] < tol, (k, rec["loss_rel_err"][k], rec["steps"][0][k], rec["oracle"][k])
+    print("X1a per-term gradient errors:", rec["term_grad_rel_err"])
     assert rec["grad_rel_err_delta"] < 1e-5 and rec["grad_rel_err_occ_w"] < 1e-5, rec
 
 
-def test_reference_diffrender_optimisation_loop(reference_copy, tmp_path):
-    cwd = os.path.join(reference_copy, "diff_render", "diftet_6_subdiv", "6_optim")
-    for mode in ("leaf", "fused"):
-        out = str(tmp_path / ("x1b_%s.json" % mode))
-        _run("harness_diffrender.py", [mode, out], reference_copy, cwd, with_ref_root=False)
-        rec = json.load(open(out))
-        print("X1b", mode, json.dumps(rec)[:800])
-        assert rec["iterations"] == 3 and rec["finite"] and rec["params_changed"]
+def _write_blender_dataset(folder, n_train=6, size=64):
+    """A tiny NeRF-synthetic style data set on disk (transforms_*.json + RGBA PNGs) for 2_data/load_blender.py."""
+    import cv2
+    import numpy as np
+    os.makedirs(folder, exist_ok=True)
+    yy, xx = np.meshgrid(np.linspace(-1, 1, size), np.linspace(-1, 1, size), indexing="ij")
+    alpha = ((xx ** 2 + yy ** 2) < 0.35).astype(np.float32)
+
+    def pose(theta_deg, phi_deg=-30.0, radius=4.0):          # NeRF-synthetic camera-to-world matrix on a sphere
+        th, ph = np.deg2rad(theta_deg), np.deg2rad(phi_deg)
+        t = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, radius], [0, 0, 0, 1.0]])
+        rp = np.array([[1, 0, 0, 0], [0, np.cos(ph), -np.sin(ph), 0], [0, np.sin(ph), np.cos(ph), 0], [0, 0, 0, 1.0]])
+        rt = np.array([[np.cos(th), 0, -np.sin(th), 0], [0, 1, 0, 0], [np.sin(th), 0, np.cos(th), 0], [0, 0, 0, 1.0]])
+        return (np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1.0]]) @ rt @ rp @ t)
+
+    for split, n in (("train", n_train), ("val", 9), ("test", 9)):           # the loader keeps every 8th val / test frame
+        os.makedirs(os.path.join(folder, split), exist_ok=True)
+        frames = []
+        for i in range(n):
+            img = np.zeros((size, size, 4), dtype=np.float32)
+            img[..., 0] = alpha * (0.9 - 0.08 * i); img[..., 1] = alpha * 0.5; img[..., 2] = alpha * (0.2 + 0.08 * i); img[..., 3] = alpha
+            cv2.imwrite(os.path.join(folder, split, "r_%d.png" % i), (img * 255).astype(np.uint8))
+            frames.append({"file_path": "./%s/r_%d" % (split, i), "transform_matrix": pose(-180 + 360.0 * i / n).tolist()})
+        json.dump({"camera_angle_x": 0.6911, "frames": frames}, open(os.path.join(folder, "transforms_%s.json" % split), "w"))
+
+
+@pytest.mark.parametrize("mode", ["fused", "leaf"])
+def test_reference_diffrender_script_runs_unmodified(reference_copy, tmp_path, mode):
+    """`python -m deftet_b200.run [--leaf] optim_with_mask_subdiv_from_gridmov.py ...`: the reference's own script, __main__ block and
+    all (create_everying, two optimzie() stages of 3 iterations with a tet deletion, test views, obj export), on a res-8 grid.
+    fused: `deftet` / `deftetrneder` resolve to the drop-in model + fused renderer; leaf: the reference's own Deftet model and
+    rendermeshcolor run on the drop-in leaf modules and the Kaolin shim (kal.render.mesh.deftet_sparse_render -> csrc/render.cu)."""
+    import numpy as np
+    from deftet_b200.grid import acute_lattice_grid, write_tet_file
+    base = os.path.join(reference_copy, "diff_render", "diftet_6_subdiv")
+    os.makedirs(os.path.join(base, "data"), exist_ok=True)
+    g = acute_lattice_grid(8)
+    write_tet_file(os.path.join(base, "data", "cube_8_tet.tet"), g.vertices, g.tets)
+    data, save = str(tmp_path / "data"), str(tmp_path / "save")
+    _write_blender_dataset(os.path.join(data, "synth"))
+    os.makedirs(save)
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, STUBS]))
+    env.pop("DEFTET_REFERENCE_ROOT", None)
+    cmd = [sys.executable, "-m", "deftet_b200.run"] + (["--leaf"] if mode == "leaf" else []) + [
+        "optim_with_mask_subdiv_from_gridmov.py", "--remote", "--expname", "synth", "--datadir", data, "--savedir", save, "--tetres", "8",
+        "--sublevel", "0", "--optfixnum", "3", "--optmovnum", "3", "--deletenum", "2", "--pixelsampling", "0.5", "--i_img", "1000"]
+    r = subprocess.run(cmd, cwd=os.path.join(base, "6_optim"), env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, "script failed:\n" + r.stdout[-3000:] + "\n" + r.stderr[-6000:]
+    assert r.stdout.count("optimize_time") == 2                       # both stages (grid moving, grid fixed) ran to the end
+    ckpts = [os.path.join(d, f) for d, _, fs in os.walk(save) for f in fs if f == "deftet.pth"]
+    assert len(ckpts) == 2
+    for c in ckpts:
+        sd = torch.load(c, map_location="cpu")
+        assert all(bool(torch.isfinite(v).all()) for v in sd.values() if torch.is_tensor(v) and v.is_floating_point())
+    print("X1b", mode, "ok:", [l for l in r.stdout.splitlines() if "optimize_time" in l])
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")

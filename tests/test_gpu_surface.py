@@ -202,3 +202,23 @@ def test_grouped_nearest_neighbour_kernels_agree_with_oracle(S, monkeypatch):
         ref = orc.nearest_neighbor(q[b:b + 1, :n].cpu().numpy(), gtc[b:b + 1].cpu().numpy())
         for key, nn in outs.items():
             assert np.array_equal(nn[b, :n].cpu().numpy().astype(np.int64), ref[0]), key
+
+
+@pytest.mark.parametrize("res,G", [(8, 64), (8, 128), (12, 96), (16, 16)])
+def test_analytic_distance_faces_larger_than_a_brick(res, G):
+    """Regression (found by tests/test_gpu_scale_parity.py at res 40): when the faces are large against the search grid
+    (bounding radius + 1.25 cells > one 4-cell brick) the staged 3x3x3 neighbourhood does not contain the whole reach region;
+    the region must be clamped before a query is certified.  Coarse tet grid + fine search grid + points near and far."""
+    from deftet_b200 import surface
+    g, pos, tet, occ, f3, ft2, gt = _scene(res, 2, 31 + res)
+    table = surface.FaceTable(f3.cuda(), ft2.cuda())
+    faces, counts, overflow = surface.boundary_faces(table, occ.cuda(), 2048)
+    assert int(overflow.item()) == 0
+    gen = torch.Generator().manual_seed(G)
+    pts = torch.cat([gt, gt * (1.0 + 0.25 * torch.rand(2, gt.shape[1], 1, generator=gen)), (torch.rand(2, 2000, 3, generator=gen) - 0.5)], dim=1)
+    soup, cd, cf = surface.closest_faces(pos.cuda(), faces, counts, pts.cuda(), G)
+    cnt = counts.tolist()
+    for b in range(2):
+        d_ref, f_ref = orc.point_face_distance(pts[b:b + 1].numpy(), soup[b:b + 1, :cnt[b]].cpu().numpy())
+        assert np.array_equal(cf[b].cpu().numpy(), f_ref.reshape(-1))
+        assert np.array_equal(cd[b].cpu().numpy(), d_ref.reshape(-1))

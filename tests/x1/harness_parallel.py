@@ -129,6 +129,9 @@ for step in range(2):
     occ = occ_loss.mean()
     deform_loss = sum(terms[k] * LAMBDA[k] for k in terms)
     loss = occ * LAMBDA["occ"] + deform_loss * LAMBDA["deform"]
+    if step == 0 and n_dev == 1:          # per-term gradients w.r.t. the shared vertex offsets (diagnostics for the oracle comparison)
+        term_grads = {k: torch.autograd.grad(v, model.delta, retain_graph=True, allow_unused=True)[0] for k, v in terms.items()}
+        term_grads = {k: (torch.zeros_like(model.delta) if v is None else v).detach().cpu() for k, v in term_grads.items()}
     loss.backward()
     vals = {k: float(v) for k, v in terms.items()}
     vals.update(occ=float(occ), loss=float(loss))
@@ -178,8 +181,15 @@ if n_dev == 1:
     o_terms["lap"] = ((nei - delta) ** 2).sum(dim=-1).sum(dim=-1).mean()
     o_occ = F.binary_cross_entropy_with_logits(logits, torch.from_numpy(ref_occ)[:, idx]).mean()
     o_loss = o_occ * LAMBDA["occ"] + sum(o_terms[k] * LAMBDA[k] for k in o_terms) * LAMBDA["deform"]
-    o_loss.backward()
     rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp(min=1e-30))
+    record["term_grad_rel_err"] = {}
+    for k, v in o_terms.items():
+        if not v.requires_grad:
+            continue
+        og = torch.autograd.grad(v, delta_p, retain_graph=True, allow_unused=True)[0]
+        if og is not None and float(og.abs().max()) > 0:
+            record["term_grad_rel_err"][k] = rel(term_grads[k], og)
+    o_loss.backward()
     record["oracle"] = {k: float(v) for k, v in o_terms.items()}
     record["oracle"].update(occ=float(o_occ), loss=float(o_loss))
     record["grad_rel_err_delta"] = rel(grad_step0[0], delta_p.grad)

@@ -11,7 +11,7 @@ from oracle import native as orc, ref_cuda
 res, seed = int(sys.argv[1]) if len(sys.argv) > 1 else 40, int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 dev = torch.device("cuda:0")
 grid = acute_lattice_grid(res)
-B, P, S = 8, 1000, 100000
+B, P, S = 8, int(sys.argv[3]) if len(sys.argv) > 3 else 100000, 100000
 sc = analytic_scene(grid, B, P, S, seed, dev)
 eng = GeometryEngine(grid.centred(), grid.tets, max_boundary_faces=16384, device=dev)
 faces, counts, _ = surface.boundary_faces(eng.face_table, sc["occ"], 16384)

@@ -67,9 +67,9 @@ def main():
                               "amips0": float(out[0][0]), "vv0": float(out[2][0]), "gsum": float(out[3].double().abs().sum())}))
         os.environ.pop("DTB_ENERGY_PATH", None); os.environ.pop("DTB_ENERGY_GROUP", None)
     if "nn" in what:
-        for kern in ("thread", "brick"):
+        for kern in ("group", "brick", "thread"):
             os.environ["DTB_NN_KERNEL"] = kern
-            for G in (0, 24, 32, 40, 48, 64, 96, 128):
+            for G in ((0, 32, 40, 48, 56, 64, 80, 96, 128) if kern == "group" else (0, 48)):
                 def fn():
                     return surface.sample_and_match(sc["pos"], faces, counts, u, v, sc["gt"], G)
                 q, nn = fn()
