@@ -234,6 +234,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--serial", action="store_true", help="enqueue the loss groups on one stream (profiling)")
     ap.add_argument("--skip-ref-cuda", action="store_true", help="do not time the reference's own CUDA kernels beside ours")
+    ap.add_argument("--no-verify", action="store_true", help="skip the parity check of input set 0 against the reference's device kernels")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -409,6 +410,22 @@ def main():
                 cpu = {"value": v, "unit": "tets/ms", "cores": cores, "kind": "port", "sample": desc}
             except Exception as e:  # pragma: no cover
                 cpu = {"value": None, "unit": "tets/ms", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %s" % str(e)[:120]}
+        parity = None
+        if not args.no_verify:
+            # checker, after the timed region: every index-valued kernel of the step on input set 0 (the very tensors that were
+            # timed) against the reference's own device kernels / the non-contracted oracle (tools/parity_check.py states the contract)
+            try:
+                from tools.parity_check import verify_scene
+                rep = verify_scene(eng, scenes[0], uv[0][0], uv[0][1], strict=False)
+                parity = rep if "unavailable" in rep else {
+                    "ok": rep["ok"], "failures": rep["failures"], "A1_n_diff": rep["A1_ids"]["n_diff"], "A2_n_diff": rep["A2_ids"]["n_diff"],
+                    "A4_d_max_rel": rep["A4"]["d_max_rel"], "A4_points_not_equal_to_oracle": rep["A4"]["n_not_oracle"],
+                    "A4_fma_sensitive_points": rep["A4"]["n_fma_sensitive"], "A4_bwd_max_rel": rep["A4"]["bwd_max_rel"],
+                    "A4_engine_bwd_max_rel": rep["A4"]["engine_bwd_max_rel"], "A5_identical": rep["A5"]["identical"],
+                    "A6_A8": rep.get("A6_A8"), "boundary_faces": rep["F_b"],
+                    "against": "reference CUDA kernels (oracle/_ref/kernels_cuda, sm_100a build) + non-contracted C oracle, input set 0"}
+            except Exception as e:  # pragma: no cover
+                parity = {"unavailable": "failed: %s" % str(e)[:200]}
         ref_cuda_leg = None
         if not args.skip_ref_cuda and world == 1:
             try:
@@ -421,7 +438,7 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "tets/ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "reference_cuda": ref_cuda_leg,
-                "loss": loss_value}
+                "parity": parity, "loss": loss_value}
         print(json.dumps(line))
 
 

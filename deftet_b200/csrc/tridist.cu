@@ -532,8 +532,10 @@ __device__ __forceinline__ void tri_grad(const float* face, const float* p, floa
         float t = xdiv(xdot(PA, BA), div_nz(xdot(BA, BA)));
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            float q = A[k] * (1.f - t) + B[k] * t;
-            g9[i1 * 3 + k] = scale * (2.f * (q - p[k]) * t);
+            // non-contracted like the source (_back.cu:309-315): q - p cancels to ~sqrt(d), so an FMA here shows up as a relative
+            // error of up to 1e-3 in the gradient of points that lie almost on the surface (found by the res-70 scale parity run)
+            float q = xadd(xmul(A[k], xsub(1.f, t)), xmul(B[k], t));
+            g9[i1 * 3 + k] = scale * (2.f * xsub(q, p[k]) * t);
         }
     } else if (h.type == 2) {
         int iv = h.idx;

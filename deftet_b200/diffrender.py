@@ -9,7 +9,7 @@ Same class / method names, argument meaning and return tuples as the reference, 
     (``topology.project_faces``) feeding the fused rasterizer+compositor (``render.render_composite``), so neither the (B,P,*)
     per-vertex intermediates nor the (B,P,K,d) layer tensor are ever written; any other ``renderfunc`` gets the reference's
     per-vertex tensors;
-  * ``saveobj`` (mesh export for visualisation) is not part of the hot path and is not provided.
+  * ``saveobj`` (mesh export for visualisation) writes the reference's `tet-geo-*` / `tet-color-*` OBJ files from host-side array code.
 """
 from __future__ import annotations
 
@@ -261,5 +261,43 @@ class Deftet(nn.Module):
         self.updategeometry(m["tets"].detach())
 
     def saveobj(self, savedir, prefix, processfunc):
-        raise NotImplementedError("mesh export (3_model/deftet.py:501-557) is visualisation, outside the accelerated path; "
-                                  "use the reference's utils_tetsv.save_tet_face on tensor2ndarray() output")
+        """Mesh export of 3_model/deftet.py:503-557: for thresholds 0.005 / 0.05 / 0.15 / 0.25 the tet faces that separate a tet with
+        occupancy > 2*thres from a neighbour (or the outside, occupancy 0) whose occupancy differs by more than thres
+        (``get_face_use_occ``, utils_tetsv.py:77-128), as `tet-geo-*.obj` (``save_tet_face``: 3 vertices per triangle, winding 1-3-2)
+        and `tet-color-*.obj` (per-vertex BGR->RGB colours appended).  Tet occupancy = max of its vertex weights.  Not hot-path work:
+        the neighbour occupancies come from the GPU A12 builder, the rest is host-side array code and text output."""
+        from . import builders
+        with torch.no_grad():
+            pts = self.get_point(True)
+            w, col = processfunc(pts, self.get_feat())
+            tet = self._tet32.long()
+            T = tet.shape[0]
+            occ = w.reshape(-1)[tet].max(dim=1).values                                   # (T,)
+            nocc = torch.zeros(T, 4, device=tet.device, dtype=occ.dtype)                   # neighbour occupancy per local face slot
+            rows = builders.tet_adj_share(self._tet32, pts.shape[0]).long()                # (2 n_shared, 3): tet, neighbour, slot
+            if rows.numel():
+                nocc[rows[:, 0], rows[:, 2]] = occ[rows[:, 1]]
+            corner = torch.tensor([[0, 1, 2], [1, 0, 3], [2, 3, 0], [3, 2, 1]], device=tet.device)      # slot -> (a, b, c) of the face
+            tri_v = tet[:, corner]                                                         # (T,4,3) vertex ids
+            pts_c, col_c = pts.detach().cpu().numpy(), col.detach().cpu().numpy()[:, ::-1]
+            for thres in (0.005, 0.05, 0.15, 0.25):
+                keep = ((nocc - occ.unsqueeze(1)).abs() > thres) & (occ.unsqueeze(1) > 2 * thres)
+                # the reference concatenates the four slot masks over all tets in (tet, slot) order
+                ids = tri_v[keep].cpu().numpy()                                            # (n,3)
+                n = ids.shape[0]
+                fidx = np.arange(n) * 3
+                flines = np.stack([fidx + 1, fidx + 3, fidx + 2], axis=1)
+                xyz = pts_c[ids.reshape(-1)]
+                with open("%s/tet-geo-%s-thres-%.3f.obj" % (savedir, prefix, thres), "w") as f:
+                    out = []
+                    for k in range(n):
+                        out.extend("v %f %f %f\n" % tuple(xyz[3 * k + i]) for i in range(3))
+                        out.append("f %d %d %d\n" % tuple(flines[k]))
+                    f.write("".join(out))
+                rgb = col_c[ids.reshape(-1)]
+                with open("%s/tet-color-%s-thres-%.3f.obj" % (savedir, prefix, thres), "w") as f:
+                    out = []
+                    for k in range(n):
+                        out.extend("v %f %f %f %f %f %f\n" % (tuple(xyz[3 * k + i]) + tuple(rgb[3 * k + i])) for i in range(3))
+                        out.append("f %d %d %d\n" % tuple(flines[k]))
+                    f.write("".join(out))
