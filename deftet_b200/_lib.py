@@ -96,6 +96,15 @@ def check(rc: int, what: str = ""):
         raise DeftetB200Error("%s failed (code %d): %s" % (what or "deftet_b200 call", rc, (msg or b"").decode()))
 
 
+def aligned(t):
+    """Contiguous tensor at a 16-byte aligned address.  The kernels read index / matrix / coordinate arrays with 16-byte vector
+    loads and TMA bulk copies; tensors that are views into a packed buffer -- nn.DataParallel hands every replica its parameters
+    as slices of ONE coalesced broadcast buffer (train_multigpu.py:105-110,136-140 makes inverse_v such a parameter) -- are only
+    element-aligned and get a private copy here."""
+    t = t.contiguous()
+    return t.clone() if (t.data_ptr() & 15) else t
+
+
 def ptr(t):
     """Device (or host) address of a torch tensor / None -> NULL."""
     if t is None:

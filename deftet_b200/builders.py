@@ -37,7 +37,7 @@ def _tet32(tet, device=None):
     if device is not None:
         tet = tet.to(device)
     _lib.require_cuda(tet)
-    return tet.to(torch.int32).contiguous()
+    return _lib.aligned(tet.to(torch.int32))
 
 
 def _ws(n, dev):

@@ -27,6 +27,10 @@ int check_cuda(cudaError_t e, const char* what);
         if (!(cond)) { dtb::set_error(__VA_ARGS__); return dtb::DTB_EINVAL; } \
     } while (0)
 
+// arrays read with 16-byte vector loads / TMA bulk copies: a misaligned pointer must come back as an error, not as a device fault
+#define DTB_ALIGNED16(p) ((((size_t)(p)) & 15) == 0)
+#define DTB_REQUIRE_ALIGNED16(p, what) DTB_REQUIRE(DTB_ALIGNED16(p), "%s must be 16-byte aligned (got %p)", what, (const void*)(p))
+
 // ---- optional per-kernel CUDA-event timing (bench.py roofline leg; off by default, never on under graph capture) ----
 enum ProfTag { PROF_ENERGIES_FWD = 0, PROF_ENERGIES_BWD, PROF_PIT_TET, PROF_NN_QUERY, PROF_PFD_FORWARD, PROF_BARY_BWD, PROF_NTAGS };
 void prof_begin(int tag, cudaStream_t st);

@@ -292,6 +292,9 @@ static int energies_forward_impl(const float* pos, const float* soup, const int3
     DTB_REQUIRE(B > 0 && T > 0, "tet_energies: empty batch or grid (B=%d T=%d)", B, T);
     DTB_REQUIRE(stats != nullptr, "tet_energies: stats buffer (B*8 doubles) is required");
     DTB_REQUIRE(!(flags & DTB_ENERGY_AMIPS) || inv_v, "tet_energies: AMIPS requested without inverse_v");
+    DTB_REQUIRE_ALIGNED16(tet, "tet_energies: tet");
+    DTB_REQUIRE_ALIGNED16(inv_v, "tet_energies: inverse_v");
+    DTB_REQUIRE_ALIGNED16(soup, "tet_energies: tet_bxfx4x3");
     float* vol = nullptr;
     if (flags & DTB_ENERGY_VOLUME) {
         if (workspace_bytes < dtb_tet_energies_workspace(B, V, T) || !workspace) {
@@ -348,6 +351,8 @@ extern "C" int dtb_tet_energies_backward(const float* pos, const int32_t* tet, c
                                          float* grad_pos, void* stream) {
     DTB_REQUIRE(pos && tet && grad_pos && stats, "tet_energies_backward: null argument");
     DTB_REQUIRE(B > 0 && T > 0, "tet_energies_backward: empty batch or grid");
+    DTB_REQUIRE_ALIGNED16(tet, "tet_energies_backward: tet");
+    DTB_REQUIRE_ALIGNED16(inv_v, "tet_energies_backward: inverse_v");
     cudaStream_t st = (cudaStream_t)stream;
     int tiles = cdiv(T, E_TILE);
     IndexedSrc s{pos, V};
@@ -364,6 +369,9 @@ extern "C" int dtb_tet_energies_backward_soup(const float* tet_bxfx4x3, const fl
                                               float* grad_soup, void* stream) {
     DTB_REQUIRE(tet_bxfx4x3 && grad_soup && stats, "tet_energies_backward_soup: null argument");
     DTB_REQUIRE(B > 0 && T > 0, "tet_energies_backward_soup: empty batch or grid");
+    DTB_REQUIRE_ALIGNED16(tet_bxfx4x3, "tet_energies_backward_soup: tet_bxfx4x3");
+    DTB_REQUIRE_ALIGNED16(grad_soup, "tet_energies_backward_soup: grad_soup");
+    DTB_REQUIRE_ALIGNED16(inv_v, "tet_energies_backward_soup: inverse_v");
     cudaStream_t st = (cudaStream_t)stream;
     int tiles = cdiv(T, E_TILE);
     SoupSrc s{tet_bxfx4x3, T};
@@ -376,6 +384,7 @@ extern "C" int dtb_tet_energies_backward_soup(const float* tet_bxfx4x3, const fl
 extern "C" int dtb_tet_inverse_v(const float* pos0, const int32_t* tet, int V, int T, float* inv_v, void* stream) {
     (void)V;
     DTB_REQUIRE(pos0 && tet && inv_v, "tet_inverse_v: null argument");
+    DTB_REQUIRE_ALIGNED16(tet, "tet_inverse_v: tet");
     if (T == 0) return DTB_OK;
     inverse_v_kernel<<<cdiv(T, 256), 256, 0, (cudaStream_t)stream>>>(pos0, tet, T, inv_v);
     DTB_LAUNCH_CHECK("inverse_v");
@@ -389,6 +398,8 @@ extern "C" int dtb_tet_energies_backward_v4(const float* pos, const int32_t* tet
                                             float* grad_pos4, void* stream) {
     DTB_REQUIRE(pos && tet && grad_pos4 && stats, "tet_energies_backward_v4: null argument");
     DTB_REQUIRE(B > 0 && T > 0, "tet_energies_backward_v4: empty batch or grid");
+    DTB_REQUIRE_ALIGNED16(tet, "tet_energies_backward_v4: tet");
+    DTB_REQUIRE_ALIGNED16(inv_v, "tet_energies_backward_v4: inverse_v");
     DTB_REQUIRE((((size_t)grad_pos4) & 15) == 0, "tet_energies_backward_v4: grad_pos4 must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     int tiles = cdiv(T, E_TILE);

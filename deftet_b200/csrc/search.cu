@@ -552,6 +552,8 @@ extern "C" int dtb_point_in_tet(const float* pos, const int32_t* tet, const floa
                                 float* cond, float* bary, void* workspace, size_t workspace_bytes, void* stream) {
     if (P == 0) return DTB_OK;
     DTB_REQUIRE(pos && tet && points, "point_in_tet: null argument");
+    DTB_REQUIRE_ALIGNED16(tet, "point_in_tet: tet");
+    DTB_REQUIRE_ALIGNED16(bary, "point_in_tet: bary");
     PitIndexed src{pos, tet, V, T};
     return point_in_tet_impl(src, points, B, T, P, G, cond, bary, workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -560,6 +562,8 @@ extern "C" int dtb_point_in_tet_soup(const float* tet_bxfx4x3, const float* poin
                                      float* bary, void* workspace, size_t workspace_bytes, void* stream) {
     if (P == 0) return DTB_OK;
     DTB_REQUIRE(tet_bxfx4x3 && points, "point_in_tet_soup: null argument");
+    DTB_REQUIRE_ALIGNED16(tet_bxfx4x3, "point_in_tet_soup: tet_bxfx4x3");
+    DTB_REQUIRE_ALIGNED16(bary, "point_in_tet_soup: bary");
     PitSoup src{tet_bxfx4x3, T};
     return point_in_tet_impl(src, points, B, T, P, G, cond, bary, workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -569,6 +573,8 @@ extern "C" int dtb_tet_barycentric_backward(const float* pos, const int32_t* tet
                                             float* grad_points, void* stream) {
     (void)T;
     DTB_REQUIRE(pos && tet && points && cond && g_w, "tet_barycentric_backward: null argument");
+    DTB_REQUIRE_ALIGNED16(tet, "tet_barycentric_backward: tet");
+    DTB_REQUIRE_ALIGNED16(g_w, "tet_barycentric_backward: g_w");
     DTB_REQUIRE(grad_stride == 3 || (grad_stride == 4 && (((size_t)grad_pos) & 15) == 0), "tet_barycentric_backward: grad_stride must be 3, or 4 with a 16-byte aligned buffer");
     if (P == 0 || B == 0) return DTB_OK;
     dim3 grid(cdiv(P, 256), B);
@@ -681,6 +687,8 @@ extern "C" int dtb_tet_interpolate_forward(const float* field, const int32_t* te
                                            int P, float* out, void* stream) {
     if (P == 0 || B == 0) return DTB_OK;
     DTB_REQUIRE(field && tet && cond && bary && out && C > 0, "tet_interpolate_forward: bad argument");
+    DTB_REQUIRE_ALIGNED16(tet, "tet_interpolate_forward: tet");
+    DTB_REQUIRE_ALIGNED16(bary, "tet_interpolate_forward: bary");
     dim3 grid(cdiv(P, 256), B);
     interp_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(field, tet, V, C, cond, bary, P, out);
     DTB_LAUNCH_CHECK("interp_fwd");
@@ -691,6 +699,9 @@ extern "C" int dtb_tet_interpolate_backward(const float* field, const int32_t* t
                                             int B, int V, int C, int P, float* g_field, float* g_bary, void* stream) {
     if (P == 0 || B == 0) return DTB_OK;
     DTB_REQUIRE(field && tet && cond && bary && g_out && C > 0, "tet_interpolate_backward: bad argument");
+    DTB_REQUIRE_ALIGNED16(tet, "tet_interpolate_backward: tet");
+    DTB_REQUIRE_ALIGNED16(bary, "tet_interpolate_backward: bary");
+    DTB_REQUIRE_ALIGNED16(g_bary, "tet_interpolate_backward: g_bary");
     dim3 grid(cdiv(P, 256), B);
     interp_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(field, tet, V, C, cond, bary, P, g_out, g_field, g_bary);
     DTB_LAUNCH_CHECK("interp_bwd");

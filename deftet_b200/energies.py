@@ -18,14 +18,14 @@ AMIPS, EDGE, VOLUME, ALL = 1, 2, 4, 7
 
 
 def _f32c(t):
-    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+    return _lib.aligned(t if t.dtype == torch.float32 else t.float())
 
 
 def tet_inverse_v(init_pos: torch.Tensor, tet: torch.Tensor) -> torch.Tensor:
     """(T,3,3) inverse of the 20x-scaled rest offset matrix; singular -> identity (deftet.py:205-233,300-318)."""
     _lib.require_cuda(init_pos, tet)
     pos = _f32c(init_pos)
-    tet32 = tet.to(torch.int32).contiguous()
+    tet32 = _lib.aligned(tet.to(torch.int32))
     T = tet32.shape[0]
     out = torch.empty(T, 3, 3, device=pos.device, dtype=torch.float32)
     with torch.cuda.device(pos.device):
@@ -160,7 +160,7 @@ def tet_energies(pos, tet32, inv_v, flags=ALL, tiles=None):
     if tet32.dtype != torch.int32:
         tet32 = tet32.to(torch.int32)
     _lib.require_cuda(pos, tet32)
-    tet32 = tet32.contiguous()
+    tet32 = _lib.aligned(tet32)
     inv = None if inv_v is None else _f32c(inv_v)
     if not _use_tiled():
         return _TetEnergies.apply(pos, tet32, inv, int(flags))
@@ -174,7 +174,7 @@ def tet_energies_direct(pos, tet32, inv_v, flags=ALL):
     if tet32.dtype != torch.int32:
         tet32 = tet32.to(torch.int32)
     _lib.require_cuda(pos, tet32)
-    return _TetEnergies.apply(pos, tet32.contiguous(), None if inv_v is None else _f32c(inv_v), int(flags))
+    return _TetEnergies.apply(pos, _lib.aligned(tet32), None if inv_v is None else _f32c(inv_v), int(flags))
 
 
 class _SoupEnergies(torch.autograd.Function):

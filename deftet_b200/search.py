@@ -32,7 +32,7 @@ def _search_sigs(lib, sig):
 
 
 def _f32c(t):
-    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+    return _lib.aligned(t if t.dtype == torch.float32 else t.float())
 
 
 # --------------------------------------------------------------------------------------------------- A1
@@ -102,7 +102,7 @@ class _PointInTet(torch.autograd.Function):
 def point_in_tet(pos, tet, points, grid_res=0):
     if tet.dtype != torch.int32:
         tet = tet.to(torch.int32)
-    return _PointInTet.apply(pos, tet.contiguous(), points, int(grid_res))
+    return _PointInTet.apply(pos, _lib.aligned(tet), points, int(grid_res))
 
 
 class _TetInterpolate(torch.autograd.Function):
@@ -137,7 +137,7 @@ def tet_interpolate(field_bxvxc, tet, cond, bary):
     """Interpolate a per-vertex field at the query points located by ``point_in_tet``: -> (B,P,C)."""
     if tet.dtype != torch.int32:
         tet = tet.to(torch.int32)
-    return _TetInterpolate.apply(field_bxvxc, tet.contiguous(), cond.contiguous(), bary)
+    return _TetInterpolate.apply(field_bxvxc, _lib.aligned(tet), cond.contiguous(), bary)
 
 
 class _MaskedMSE(torch.autograd.Function):

@@ -40,7 +40,7 @@ def _surface_sigs(lib, sig):
 
 
 def _i32c(t):
-    return t.contiguous() if t.dtype == torch.int32 else t.to(torch.int32).contiguous()
+    return _lib.aligned(t if t.dtype == torch.int32 else t.to(torch.int32))
 
 
 def _ws(nbytes, dev):

@@ -170,3 +170,40 @@ def test_pybind_shaped_extension_objects(monkeypatch):
     assert np.array_equal(cond.cpu().numpy(), orc.point_in_tet(soup.numpy(), q.numpy()))
     with pytest.raises(RuntimeError):
         cc_mod.check_condition_cuda_tet_base.backward()
+
+
+def test_misaligned_parameter_views_are_accepted_and_raw_pointers_rejected():
+    """nn.DataParallel gives every replica its parameters as slices of ONE coalesced broadcast buffer, so `inverse_v` (a parameter in
+    train_multigpu.py:105-110) arrives 4-byte aligned on the non-primary devices; the kernels read it with TMA bulk copies.  Found by
+    the 2-GPU run of the reference's ParallelWrapper (a device fault, 'misaligned address').  The host mirror must copy such views,
+    and the C ABI must answer a misaligned pointer with an error code, never with a fault."""
+    import ctypes as C
+    from deftet_b200 import _lib, energies
+    g, pos, tet = deformed_grid(8, 2, seed=3)
+    dev = torch.device("cuda")
+    tet32 = tet.to(dev).to(torch.int32).contiguous()
+    inv = energies.tet_inverse_v(torch.from_numpy(g.centred()).to(dev), tet32)
+    T = tet32.shape[0]
+    packed = torch.zeros(3 + inv.numel(), device=dev)                         # 12-byte offset: what a coalesced buffer does
+    inv_view = packed[3:].view(T, 3, 3)
+    inv_view.copy_(inv)
+    tet_packed = torch.zeros(1 + tet32.numel(), device=dev, dtype=torch.int32)
+    tet_view = tet_packed[1:].view(T, 4)
+    tet_view.copy_(tet32)
+    assert inv_view.data_ptr() % 16 != 0 and tet_view.data_ptr() % 16 != 0
+    p = pos.to(dev)
+    ref = energies.tet_energies(p, tet32, inv)
+    out = energies.tet_energies(p, tet_view, inv_view)
+    for a, b in zip(ref, out):
+        assert torch.equal(a, b)
+    # the raw entry point refuses the misaligned pointer
+    L = _lib.lib()
+    B, V = p.shape[0], p.shape[1]
+    am, ed, vv = (torch.empty(B, device=dev) for _ in range(3))
+    stats = torch.zeros(B * 8, device=dev, dtype=torch.float64)
+    wsz = L.dtb_tet_energies_workspace(B, V, T)
+    ws = torch.empty(wsz, device=dev, dtype=torch.uint8)
+    rc = L.dtb_tet_energies_forward(_lib.ptr(p.contiguous()), _lib.ptr(tet32), _lib.ptr(inv_view), B, V, T, energies.ALL, _lib.ptr(am), _lib.ptr(ed),
+                                    _lib.ptr(vv), _lib.ptr(stats), _lib.ptr(ws), wsz, _lib.stream_ptr())
+    assert rc != 0 and b"16-byte aligned" in L.dtb_last_error()
+    torch.cuda.synchronize()
