@@ -41,27 +41,37 @@ class Step:
     """One forward+backward of the geometry losses; gradient lands in delta.grad (V,3)."""
 
     WEIGHTS = dict(amips=1.0, edge=1.0, volume_variance=1e6, chamfer=1.0, distance=1.0, normal=0.1, occupancy=1.0)
+    ALL = ("energies", "chamfer", "distance", "normal", "occupancy")
 
-    def __init__(self, engine, samples, Fmax, S_face):
+    def __init__(self, engine, samples, Fmax, S_face, want=None, loss_scale=1.0):
         self.eng = engine
         self.Fmax, self.S_face = Fmax, S_face
         self.delta = torch.zeros(engine.n_vert, 3, device=engine.device, requires_grad=True)
         self.samples = samples
+        self.want = tuple(want) if want is not None else self.ALL
         w = self.WEIGHTS
-        self.wvec = torch.tensor([w["amips"], w["edge"], w["volume_variance"], w["chamfer"], w["distance"], w["normal"], w["occupancy"]],
-                                 device=engine.device).unsqueeze(-1)
+        names = []
+        if "energies" in self.want:
+            names += ["amips", "edge", "volume_variance"]
+        names += [k for k in ("chamfer", "distance", "normal") if k in self.want]
+        if "occupancy" in self.want:
+            names.append("occupancy")
+        self.names = names
+        self.wvec = (torch.tensor([w[k] for k in names], device=engine.device) * loss_scale).unsqueeze(-1)
 
     def forward_backward(self, sc, u, v, concurrent=True):
         eng = self.eng
         pos = sc["pos"] + self.delta.unsqueeze(0)
-        out = eng.losses(pos, sc["occ"], sc["gt"], u, v, sc["pts"], concurrent=concurrent)
-        cond, bary = out["condition"], out["barycentric"]
-        pred = search.tet_interpolate(sc["vfield"].unsqueeze(-1), eng.tet, cond, bary).squeeze(-1)
-        occ_loss = search.located_mse(pred, sc["target"], cond)
-        terms = torch.stack([out["amips"], out["edge"], out["volume_variance"], out["chamfer"], out["distance"], out["normal"], occ_loss])
+        out = eng.losses(pos, sc["occ"], sc["gt"], u, v, sc["pts"], want=self.want, concurrent=concurrent, chamfer_targets=sc.get("gt_chamfer"))
+        if "occupancy" in self.want:
+            cond, bary = out["condition"], out["barycentric"]
+            pred = search.tet_interpolate(sc["vfield"].unsqueeze(-1), eng.tet, cond, bary).squeeze(-1)
+            out["occupancy"] = search.located_mse(pred, sc["target"], cond)
+        terms = torch.stack([out[k] for k in self.names])
         loss = (terms * self.wvec).sum()
         loss.backward()
-        return loss.detach(), out["boundary_counts"], out["boundary_overflow"]
+        zero = torch.zeros((), device=eng.device, dtype=torch.int32)
+        return loss.detach(), out.get("boundary_counts"), out.get("boundary_overflow", zero)
 
 
 # ------------------------------------------------------------------------------------------------- clocks
@@ -227,8 +237,13 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--res", type=int, default=70)
-    ap.add_argument("--batch", type=int, default=8, help="samples per GPU (weak scaling)")
+    ap.add_argument("--config", default="3", choices=["2", "3", "3s", "4", "5"],
+                    help="BASELINE.json configs: 3 = res 70, batch 8 per GPU, full loss, weak scaling (default, the metric's config); "
+                         "3s = the same with a GLOBAL batch of 8 (strong scaling, 1 sample per GPU at N=8); 2 = res 40 batch 8, occupancy "
+                         "query + AMIPS only; 4 = res 100 batch 4 with adjacency rebuild + vertex collapse inside the step; "
+                         "5 = diff_render, 64 views of 800x800 sharded over the ranks")
+    ap.add_argument("--res", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (weak scaling)")
     ap.add_argument("--points", type=int, default=100000)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -240,12 +255,35 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.config in ("4", "5") and args.impl == "ours":
+        from tools import bench_extra
+        return (bench_extra.run_config4 if args.config == "4" else bench_extra.run_config5)(args, rank, world, local_rank, ClockSampler)
+    if args.config in ("4", "5"):
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "the CPU port arm is defined for configs 2/3/3s only"}))
+        return
+    if args.config != "3":
+        args.skip_cpu = args.skip_ref_cuda = args.no_verify = True      # those legs are sized for the metric's own configuration
     from deftet_b200.grid import acute_lattice_grid
+    scaling, want = "weak", None
+    if args.config == "2":
+        args.res, args.batch = args.res or 40, args.batch or 8
+        want = ("energies", "occupancy")
+        what = "occupancy query (point-in-tet + barycentric backward) + AMIPS/edge/volume energies fwd+bwd (BASELINE.json configs[1])"
+    elif args.config == "3s":
+        args.res = args.res or 70
+        assert 8 % world == 0, "strong scaling of the global batch of 8 needs N in {1,2,4,8}"
+        args.batch = 8 // world
+        scaling = "strong"
+        what = "full surf+chamfer+AMIPS loss + point-in-tet, GLOBAL batch 8 split over the ranks (BASELINE.json configs[2], strong scaling)"
+    else:
+        args.res, args.batch = args.res or 70, args.batch or 8
+        what = "full surf+chamfer+AMIPS loss + point-in-tet (BASELINE.json configs[2])"
     grid = acute_lattice_grid(args.res)
     B, P, S, T, V = args.batch, args.points, args.points, grid.n_tet, grid.n_vert
-    config = {"workload": "res=%d batch %d/GPU, full surf+chamfer+AMIPS loss + point-in-tet (BASELINE.json configs[2])" % (args.res, B),
+    config = {"workload": "res=%d batch %d/GPU, %s" % (args.res, B, what),
               "grid": "synthetic acute lattice V=%d T=%d" % (V, T), "global_batch": B * max(world, 1), "query_points": P,
-              "gt_points": S, "parallelism": "dp%d" % max(world, 1)}
+              "gt_points": S, "parallelism": "dp%d" % max(world, 1), "bench_config": args.config}
 
     if args.impl == "reference":
         if rank != 0:
@@ -257,7 +295,7 @@ def main():
         v = float(np.median(vals))
         line = {"impl": "reference", "metric": "tets/ms fwd+bwd (occ+AMIPS+chamfer) res-%d" % args.res, "value": v, "unit": "tets/ms",
                 "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": B * T / v, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "tets/ms", "cores": cores, "kind": "port", "sample": desc},
                 "e2e": {"value": v, "unit": "tets/ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
@@ -281,7 +319,7 @@ def main():
           for _ in range(NSETS)]
     set_bytes = sum(t.numel() * 4 for t in scenes[0].values()) + 2 * B * Fmax * S_face * 4
     config["l2"] = "inputs rotate over %d sets of %.0f MB (> 126 MB L2 in total)" % (NSETS, set_bytes / 1e6)
-    step = Step(eng, scenes, Fmax, S_face)
+    step = Step(eng, scenes, Fmax, S_face, want=want)
 
     def run_eager(s):
         step.delta.grad = None
@@ -434,7 +472,7 @@ def main():
                 ref_cuda_leg = {"unavailable": "failed: %s" % str(e)[:160]}
         config["graph"] = config.get("graph", "cuda graph replay" if graphs is not None else "eager")
         line = {"metric": "tets/ms fwd+bwd (occ+AMIPS+chamfer) res-%d" % args.res, "value": value, "unit": "tets/ms", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "tets/ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "reference_cuda": ref_cuda_leg,

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) pg_bbox_kernel(const float* __restrict__ 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float x, y, z;
         load_item(items, (size_t)b * N + i, tri, x, y, z);
-        if (x == x && y == y && z == z) {
+        if (fabsf(x) <= 3.0e38f && fabsf(y) <= 3.0e38f && fabsf(z) <= 3.0e38f) {       // finite items only: one inf would blow the grid up to a single cell
             mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
             mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
         }

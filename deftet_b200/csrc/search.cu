@@ -21,7 +21,7 @@ namespace dtb {
 // ---------------------------------------------------------------------------------------------------
 // A1
 // ---------------------------------------------------------------------------------------------------
-struct FacePlane { float ax, ay, az, nx, ny, nz; bool sv; };
+struct FacePlane { float ax, ay, az, nx, ny, nz; bool sv; float dv; };
 
 // normal of (b-a)x(c-a), sign of its dot with (d-a): check_condition_tet_for.cu:105-121
 __device__ __forceinline__ FacePlane make_plane(const float* a, const float* b, const float* c, const float* d) {
@@ -35,6 +35,7 @@ __device__ __forceinline__ FacePlane make_plane(const float* a, const float* b, 
     float dx = xsub(d[0], a[0]), dy = xsub(d[1], a[1]), dz = xsub(d[2], a[2]);
     float dotv4 = xadd(xadd(xmul(f.nx, dx), xmul(f.ny, dy)), xmul(f.nz, dz));
     f.sv = dotv4 > 0.f;
+    f.dv = dotv4;
     return f;
 }
 __device__ __forceinline__ bool same_side(const FacePlane& f, float px, float py, float pz) {
@@ -68,23 +69,36 @@ struct PitSoup {
 template <typename Src>
 __global__ void __launch_bounds__(128) pit_tet_kernel(Src src, int T, int P, int G, const unsigned* __restrict__ bbox_ord,
                                                       const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
-                                                      const float4* __restrict__ sorted, int* __restrict__ hit) {
+                                                      const float4* __restrict__ sorted, int* __restrict__ hit, int* __restrict__ weak_list,
+                                                      int* __restrict__ n_weak) {
     const int b = blockIdx.y;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     float v[4][3];
     src.load(b, t, v);
+    // the four rotations (a,b,c,d),(b,a,d,c),(c,d,a,b),(d,c,b,a) of check_condition_tet_for.cu:172-175
+    FacePlane f1 = make_plane(v[0], v[1], v[2], v[3]);
+    FacePlane f2 = make_plane(v[1], v[0], v[3], v[2]);
+    FacePlane f3 = make_plane(v[2], v[3], v[0], v[1]);
+    FacePlane f4 = make_plane(v[3], v[2], v[1], v[0]);
     float mn[3], mx[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         mn[k] = fminf(fminf(v[0][k], v[1][k]), fminf(v[2][k], v[3][k]));
         mx[k] = fmaxf(fmaxf(v[0][k], v[1][k]), fmaxf(v[2][k], v[3][k]));
     }
-    // conservative inflation: the fp32 predicates can accept points a few ulps outside the exact tet
     float ext = fmaxf(fmaxf(mx[0] - mn[0], mx[1] - mn[1]), mx[2] - mn[2]);
+    // `weak`: the sign of the four dotv4 (each is +-6 x the signed volume, formed from edges no longer than 3 ext in L1) is not
+    // certain in fp32 -- zero-volume / sliver tets, NaN or inf vertices.  For such a tet the four predicates can agree for points
+    // ANYWHERE (identical vertices: every dot product is 0, both sign tests false, every point accepted,
+    // check_condition_tet_for.cu:105-121), so it is not pruned by its bounding box but handed to pit_weak_kernel (brute force).
+    if (!(fabsf(f1.dv) > 2.7e-4f * ext * ext * ext)) {
+        weak_list[(size_t)b * T + atomicAdd(n_weak + b, 1)] = t;
+        return;
+    }
+    // conservative inflation: the fp32 predicates can accept points a few ulps outside the exact tet
     float mag = fmaxf(fmaxf(fmaxf(fabsf(mn[0]), fabsf(mx[0])), fmaxf(fabsf(mn[1]), fabsf(mx[1]))), fmaxf(fabsf(mn[2]), fabsf(mx[2])));
     float margin = 1e-4f * ext + 1e-5f * mag;
-    if (!(margin == margin)) return;                         // NaN vertices never contain anything
 #pragma unroll
     for (int k = 0; k < 3; ++k) { mn[k] -= margin; mx[k] += margin; }
     GridParams g = grid_params(bbox_ord, b, G);
@@ -95,11 +109,6 @@ __global__ void __launch_bounds__(128) pit_tet_kernel(Src src, int T, int P, int
     int x0 = cell_coord(mn[0], g.ox, g.inv_h, G), x1 = cell_coord(mx[0], g.ox, g.inv_h, G);
     int y0 = cell_coord(mn[1], g.oy, g.inv_h, G), y1 = cell_coord(mx[1], g.oy, g.inv_h, G);
     int z0 = cell_coord(mn[2], g.oz, g.inv_h, G), z1 = cell_coord(mx[2], g.oz, g.inv_h, G);
-    // the four rotations (a,b,c,d),(b,a,d,c),(c,d,a,b),(d,c,b,a) of check_condition_tet_for.cu:172-175
-    FacePlane f1 = make_plane(v[0], v[1], v[2], v[3]);
-    FacePlane f2 = make_plane(v[1], v[0], v[3], v[2]);
-    FacePlane f3 = make_plane(v[2], v[3], v[0], v[1]);
-    FacePlane f4 = make_plane(v[3], v[2], v[1], v[0]);
     int* hb = hit + (size_t)b * P;
     const size_t cbase = (size_t)b * G * G * G;
     for (int z = z0; z <= z1; ++z)
@@ -114,6 +123,34 @@ __global__ void __launch_bounds__(128) pit_tet_kernel(Src src, int T, int P, int
                 if (s1 == s2 && s2 == s3 && s3 == s4) atomicMin(hb + __float_as_int(q.w), t);
             }
         }
+}
+
+// Tets whose orientation is numerically uncertain (see make_plane) against ALL points of their sample.  Launched with a fixed grid
+// behind pit_tet_kernel; returns at once when the list is empty (every well-formed grid).  Points that the binning could not place
+// (non-finite coordinates) are covered as well: the loop runs over the original point array.
+template <typename Src>
+__global__ void __launch_bounds__(256) pit_weak_kernel(Src src, int T, const float* __restrict__ points, int P, const int* __restrict__ weak_list,
+                                                       const int* __restrict__ n_weak, int* __restrict__ hit) {
+    const int b = blockIdx.y;
+    const int n = n_weak[b];
+    if (n == 0) return;
+    const float* pb = points + (size_t)b * P * 3;
+    int* hb = hit + (size_t)b * P;
+    for (int e = blockIdx.x; e < n; e += gridDim.x) {
+        const int t = weak_list[(size_t)b * T + e];
+        float v[4][3];
+        src.load(b, t, v);
+        FacePlane f1 = make_plane(v[0], v[1], v[2], v[3]);
+        FacePlane f2 = make_plane(v[1], v[0], v[3], v[2]);
+        FacePlane f3 = make_plane(v[2], v[3], v[0], v[1]);
+        FacePlane f4 = make_plane(v[3], v[2], v[1], v[0]);
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            const float qx = pb[(size_t)i * 3], qy = pb[(size_t)i * 3 + 1], qz = pb[(size_t)i * 3 + 2];
+            bool s1 = same_side(f1, qx, qy, qz), s2 = same_side(f2, qx, qy, qz);
+            bool s3 = same_side(f3, qx, qy, qz), s4 = same_side(f4, qx, qy, qz);
+            if (s1 == s2 && s2 == s3 && s3 == s4) atomicMin(hb + i, t);
+        }
+    }
 }
 
 // bary_centric_tet (utils/tet_utils.py:28-45): ratios of scalar triple products
@@ -136,12 +173,30 @@ __device__ __forceinline__ void bary_weights(const float v[4][3], const float* p
 }
 
 template <typename Src>
-__global__ void __launch_bounds__(256) pit_finalize_kernel(Src src, const float* __restrict__ points, int P, const int* __restrict__ hit,
+__global__ void __launch_bounds__(256) pit_finalize_kernel(Src src, int T, const float* __restrict__ points, int P, const int* __restrict__ hit,
                                                            float* __restrict__ cond, float* __restrict__ bary) {
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     int t = hit[(size_t)b * P + i];
+    {
+        // a point with a non-finite coordinate cannot be binned, and the reference's predicates treat it in their own way (NaN: both
+        // sign tests false -> the first consistently oriented tet "contains" it): answer it with the reference's own serial scan
+        const float* p = points + ((size_t)b * P + i) * 3;
+        const float s = p[0] + p[1] + p[2];
+        if (!(fabsf(s) <= 3.0e38f)) {
+            t = 0x7f7f7f7f;
+            for (int k = 0; k < T; ++k) {
+                float v[4][3];
+                src.load(b, k, v);
+                FacePlane f1 = make_plane(v[0], v[1], v[2], v[3]), f2 = make_plane(v[1], v[0], v[3], v[2]);
+                FacePlane f3 = make_plane(v[2], v[3], v[0], v[1]), f4 = make_plane(v[3], v[2], v[1], v[0]);
+                bool s1 = same_side(f1, p[0], p[1], p[2]), s2 = same_side(f2, p[0], p[1], p[2]);
+                bool s3 = same_side(f3, p[0], p[1], p[2]), s4 = same_side(f4, p[0], p[1], p[2]);
+                if (s1 == s2 && s2 == s3 && s3 == s4) { t = k; break; }
+            }
+        }
+    }
     bool found = t != 0x7f7f7f7f;
     if (cond) cond[(size_t)b * P + i] = found ? (float)t : -1.0f;
     if (bary) {
@@ -518,7 +573,8 @@ extern "C" int dtb_point_in_tet_grid_res(int T, int P) {
 }
 extern "C" size_t dtb_point_in_tet_workspace(int B, int P, int T, int G) {
     if (G <= 0) G = dtb_point_in_tet_grid_res(T, P);
-    return pointgrid_workspace_bytes(B, P, G, false, false) + align_up((size_t)B * P * sizeof(int), 256);
+    return pointgrid_workspace_bytes(B, P, G, false, false) + align_up((size_t)B * P * sizeof(int), 256) +
+           align_up((size_t)B * T * sizeof(int), 256) + align_up((size_t)B * sizeof(int), 256);
 }
 
 template <typename Src>
@@ -531,19 +587,25 @@ static int point_in_tet_impl(Src src, const float* points, int B, int T, int P, 
     PointGrid pg;
     pointgrid_carve(pg, B, P, G, false, false, ws);
     int* hit = ws.take<int>((size_t)B * P);
+    int* weak_list = ws.take<int>((size_t)B * T);
+    int* n_weak = ws.take<int>(B);
     if (!ws.ok || !workspace) { set_error("point_in_tet: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return DTB_EWORKSPACE; }
     int rc = pointgrid_build(pg, points, false, st);
     if (rc) return rc;
     DTB_CUDA(cudaMemsetAsync(hit, 0x7f, (size_t)B * P * sizeof(int), st));    // 0x7f7f7f7f: larger than any tet id
+    DTB_CUDA(cudaMemsetAsync(n_weak, 0, (size_t)B * sizeof(int), st));
     if (T > 0) {
         dim3 grid(cdiv(T, 128), B);
         prof_begin(PROF_PIT_TET, st);
-        pit_tet_kernel<Src><<<grid, 128, 0, st>>>(src, T, P, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, hit);
+        pit_tet_kernel<Src><<<grid, 128, 0, st>>>(src, T, P, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, hit, weak_list, n_weak);
         DTB_LAUNCH_CHECK("pit_tet");
         prof_end(PROF_PIT_TET, st);
+        dim3 gw(296, B);
+        pit_weak_kernel<Src><<<gw, 256, 0, st>>>(src, T, points, P, weak_list, n_weak, hit);
+        DTB_LAUNCH_CHECK("pit_weak");
     }
     dim3 gf(cdiv(P, 256), B);
-    pit_finalize_kernel<Src><<<gf, 256, 0, st>>>(src, points, P, hit, cond, bary);
+    pit_finalize_kernel<Src><<<gf, 256, 0, st>>>(src, T, points, P, hit, cond, bary);
     DTB_LAUNCH_CHECK("pit_finalize");
     return DTB_OK;
 }

@@ -32,6 +32,7 @@ class GeometryEngine:
         self.max_boundary_faces = int(max_boundary_faces)
         self.samples_per_face = int(samples_per_face)
         self._streams = None
+        self._ovf_host, self._ovf_event = None, None            # lazily checked capacity flag of the previous call (see losses)
 
     @property
     def tet_tiles(self):
@@ -49,15 +50,41 @@ class GeometryEngine:
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(4)]
         return self._streams
 
+    def _watch_overflow(self, overflow):
+        """The boundary faces are compacted into a fixed-capacity buffer (no host synchronisation, graph capturable); when a sample has
+        more than `max_boundary_faces` of them the surface losses would silently be computed on a truncated surface (the reference's
+        get_boundary_index never truncates).  The flag travels to pinned host memory asynchronously and is looked at -- without
+        blocking -- at the start of a later call."""
+        if torch.cuda.is_current_stream_capturing():
+            return
+        if self._ovf_host is None:
+            self._ovf_host = torch.zeros(1, dtype=overflow.dtype).pin_memory()
+            self._ovf_event = torch.cuda.Event()
+        elif not self._ovf_event.query():
+            return                                            # the previous flag is still in flight: keep watching that one
+        self._ovf_host.copy_(overflow.reshape(1), non_blocking=True)
+        self._ovf_event.record(torch.cuda.current_stream(self.device))
+
+    def _raise_on_earlier_overflow(self):
+        if torch.cuda.is_current_stream_capturing():           # (an event query would invalidate the capture)
+            return
+        if self._ovf_event is not None and self._ovf_event.query() and int(self._ovf_host[0]) != 0:
+            self._ovf_host.zero_()
+            raise RuntimeError("GeometryEngine.losses: an earlier call found more boundary faces than max_boundary_faces=%d; its surface "
+                               "losses were computed on a truncated surface -- construct the engine with a larger capacity "
+                               "(at most face_table.n_face = %d)" % (self.max_boundary_faces, self.face_table.n_face))
+
     def losses(self, pos, occ, gt_points, u, v, query_points=None, want=("energies", "chamfer", "distance", "normal", "occupancy"),
-               concurrent=True):
+               concurrent=True, chamfer_targets=None):
         """pos (B,V,3); occ (B,T) in {0,1}; gt_points (B,S,3); u,v (B,Fmax,samples) sampling randoms;
-        query_points (B,P,3) for the point-in-tet query.  Returns a dict; every loss is (B,).
+        query_points (B,P,3) for the point-in-tet query; chamfer_targets (B,M,3): the 1-NN target set of the chamfer term when it is
+        not gt_points (a rank that holds only a slice of the GT points for the distance term).  Returns a dict; every loss is (B,).
 
         The loss groups are independent of each other (they only share `pos` and the boundary faces) and each of their
         kernels leaves most issue slots idle (profiles/), so with ``concurrent=True`` they are enqueued on side streams
         (fork after the inputs, join before returning; autograd replays the same stream assignment in backward).
         Everything stays capturable in one CUDA graph."""
+        self._raise_on_earlier_overflow()
         out = {}
         main = torch.cuda.current_stream(self.device)
         if concurrent:
@@ -85,11 +112,13 @@ class GeometryEngine:
             with fork(s_pit):
                 out["condition"], out["barycentric"] = search.point_in_tet(pos, self.tet, query_points)
                 publish(out["condition"], out["barycentric"])
-        faces, counts, overflow = surface.boundary_faces(self.face_table, occ, self.max_boundary_faces)
-        out["boundary_faces"], out["boundary_counts"], out["boundary_overflow"] = faces, counts, overflow
+        if any(k in want for k in ("chamfer", "distance", "normal", "boundary")):
+            faces, counts, overflow = surface.boundary_faces(self.face_table, occ, self.max_boundary_faces)
+            out["boundary_faces"], out["boundary_counts"], out["boundary_overflow"] = faces, counts, overflow
+            self._watch_overflow(overflow)
         if "chamfer" in want:
             with fork(s_ch):
-                out["chamfer"] = surface.surface_chamfer(pos, faces, counts, u, v, gt_points)
+                out["chamfer"] = surface.surface_chamfer(pos, faces, counts, u, v, gt_points if chamfer_targets is None else chamfer_targets)
                 publish(out["chamfer"])
         if "distance" in want:
             with fork(s_sd):

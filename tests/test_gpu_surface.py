@@ -222,3 +222,18 @@ def test_analytic_distance_faces_larger_than_a_brick(res, G):
         d_ref, f_ref = orc.point_face_distance(pts[b:b + 1].numpy(), soup[b:b + 1, :cnt[b]].cpu().numpy())
         assert np.array_equal(cf[b].cpu().numpy(), f_ref.reshape(-1))
         assert np.array_equal(cd[b].cpu().numpy(), d_ref.reshape(-1))
+
+
+def test_engine_reports_boundary_capacity_overflow():
+    """with more boundary faces than `max_boundary_faces` the surface losses are computed on a truncated surface; the engine
+    must say so (lazily, without a host synchronisation inside the step): the NEXT call raises."""
+    from deftet_b200.engine import GeometryEngine
+    g, pos, tet, occ, f3, ft2, gt = _scene(10, 2, 9)
+    eng = GeometryEngine(g.centred(), g.tets, max_boundary_faces=16, device="cuda")          # far too small on purpose
+    u = torch.rand(2, 16, 20).cuda()
+    v = torch.rand(2, 16, 20).cuda()
+    out = eng.losses(pos.cuda(), occ.cuda(), gt.cuda(), u, v, None, want=("chamfer",))
+    assert int(out["boundary_overflow"].item()) == 1
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="max_boundary_faces"):
+        eng.losses(pos.cuda(), occ.cuda(), gt.cuda(), u, v, None, want=("chamfer",))
