@@ -117,64 +117,124 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- cpu leg
-def cpu_reference_step(grid, B, P, S, seed, budget_s=20.0, threads=None):
-    """The reference's algorithms on the host (oracle port), on a bounded sample of the workload, scaled to a
-    full step.  Returns (tets_per_ms, cores, description)."""
+def _reference_deftet_class():
+    """The reference's OWN `DefTet` class (layers/DefTet/deftet.py) for the pure-PyTorch energies, imported from the packed copy of
+    the reference's python (oracle/_ref/reference_py.zip, built where /root/reference is mounted; travels to the GPU box) under
+    stubs for kaolin and the CUDA-extension wrappers.  None when the archive is absent."""
+    import importlib
+    import tempfile
+    import types
+    import zipfile
+    arc = os.path.join(ROOT, "oracle", "_ref", "reference_py.zip")
+    if not os.path.exists(arc):
+        return None
+    d = tempfile.mkdtemp(prefix="deftet_ref_py_")
+    with zipfile.ZipFile(arc) as z:
+        z.extractall(d)
+    saved = {k: sys.modules.get(k) for k in ("kaolin", "utils", "utils.tet_utils", "utils.mesh_utils", "layers", "layers.DefTet",
+                                             "layers.DefTet.check_condition_tetrahedron_base", "layers.DefTet.check_condition_tetrahedron_base.utils")}
+    try:
+        for name in ("kaolin", "utils.tet_utils", "utils.mesh_utils", "layers.DefTet.check_condition_tetrahedron_base.utils"):
+            m = types.ModuleType(name)
+            m.check_condition_f_base = None
+            sys.modules[name] = m
+        for name in ("utils", "layers", "layers.DefTet", "layers.DefTet.check_condition_tetrahedron_base"):
+            sys.modules.pop(name, None)
+        sys.path.insert(0, d)
+        mod = importlib.import_module("layers.DefTet.deftet")
+        return mod.DefTet
+    except Exception:
+        return None
+    finally:
+        if d in sys.path:
+            sys.path.remove(d)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def cpu_reference_step(grid, B, P, S, seed, threads=None, n_a1=4096):
+    """The reference's algorithms on the host cores, one bounded sample of one step of the workload:
+      * A6-A8 forward + backward, FULL batch, through the reference's own DefTet class on CPU tensors when the packed reference
+        python is present (kind "reference"), else the op-for-op restatement oracle/energies.py (kind "port");
+      * A2, A4 forward, A5: FULL size for ONE sample of the batch (the oracle port of the CUDA-only kernels, all host threads);
+      * A1: the reference's O(P T) scan for n_a1 of the P query points of one sample.
+    Returns a dict: measured wall seconds of the sample, the full-step estimate (measured parts scaled by B, A1 by B P / n_a1 --
+    the scan is independent per point) and tets/ms from that estimate."""
     from oracle import energies as orc_e
     from oracle import native as orc
     from oracle import surface as orc_s
-    from oracle import builders as orc_b
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(min(threads, 32))          # the reference's torch ops stop scaling (and thrash) beyond this
     sc = analytic_scene(grid, B, P, S, seed, "cpu")
     tet = torch.from_numpy(grid.tets)
     T = grid.n_tet
-    t_total, parts = 0.0, {}
-    # A6-A8 fwd+bwd: the reference's own pure-PyTorch path, full batch
-    inv = orc_e.tet_inverse_v(torch.from_numpy(grid.centred()), tet)
-    orc_e.energies_with_grad(sc["pos"][:1], tet, inv, (1.0, 1.0, 1e6))      # warm-up (allocator, thread pool)
+    parts, full = {}, {}
+    t_wall = time.perf_counter()
+    # ---- A6-A8 fwd+bwd, full batch
+    RefDefTet = _reference_deftet_class()
+    if RefDefTet is not None:
+        D = RefDefTet()
+        inv = D.tet_inverse_v(torch.from_numpy(grid.centred()), tet)
+
+        def energies_pass(pos):
+            p = pos.clone().requires_grad_(True)
+            soup = torch.gather(p.unsqueeze(2).expand(-1, -1, 4, -1), 1, tet.unsqueeze(0).expand(p.shape[0], -1, -1).unsqueeze(-1).expand(-1, -1, -1, 3))
+            (D.amips_energy(soup, inv) + D.edge_length(soup, pow=4) + 1e6 * D.volume_variance(soup, pow=4)).sum().backward()
+        energies_kind = "reference DefTet class (layers/DefTet/deftet.py) on CPU tensors"
+    else:
+        inv = orc_e.tet_inverse_v(torch.from_numpy(grid.centred()), tet)
+
+        def energies_pass(pos):
+            orc_e.energies_with_grad(pos, tet, inv, (1.0, 1.0, 1e6))
+        energies_kind = "restatement oracle/energies.py (packed reference python absent)"
+    energies_pass(sc["pos"][:1])                      # warm-up (allocator, thread pool)
     t0 = time.perf_counter()
-    orc_e.energies_with_grad(sc["pos"], tet, inv, (1.0, 1.0, 1e6))
-    parts["energies_full"] = time.perf_counter() - t0
-    t_total += parts["energies_full"]
+    energies_pass(sc["pos"])
+    parts["A6-A8 energies fwd+bwd, full batch"] = full["energies"] = time.perf_counter() - t0
+    # ---- A1: n_a1 points of sample 0 against all T tets
     soup = orc_e.gather_tets(sc["pos"][:1], tet).numpy()
-    # A1 brute force on n1 points of sample 0, scaled to B*P
-    n1 = max(threads * 8, 256)
+    n1 = min(n_a1, P)
     t0 = time.perf_counter()
     orc.point_in_tet(soup, sc["pts"][:1, :n1].numpy(), threads)
     dt = time.perf_counter() - t0
-    parts["point_in_tet_%dpts" % n1] = dt
-    t_total += dt * (B * P / n1)
-    # boundary of sample 0 (numpy face table) for A2/A4/A5
+    parts["A1 point-in-tet, %d of %d points of 1 sample" % (n1, P)] = dt
+    full["A1"] = dt * (B * P / n1)
+    # ---- boundary of sample 0 (numpy face table) for A2/A4/A5
     from tools.quick_time import numpy_face_table
     f3, ft2 = numpy_face_table(grid.tets, grid.n_vert)
     bnd = orc_s.get_boundary_index(torch.from_numpy(f3), torch.from_numpy(ft2), sc["occ"][:1])[0]
     Fb = int(bnd.shape[0])
     faces = orc_s.gather_faces(sc["pos"][:1], bnd)
-    # A2: n2 queries vs S points, scaled to B * 20 * Fb
-    n2 = max(threads * 64, 2048)
-    q = sc["gt"][:1, :n2] + 0.01
+    # ---- A2: all 20 F_b sampled surface points of sample 0 vs its S GT points
+    g = torch.Generator().manual_seed(seed)
+    u, v = torch.sqrt(torch.rand(1, Fb, 20, 1, generator=g)), torch.rand(1, Fb, 20, 1, generator=g)
+    q = orc_s.sample_points(faces, u, v).reshape(1, -1, 3).contiguous()
     t0 = time.perf_counter()
     orc.nearest_neighbor(q.numpy(), sc["gt"][:1].numpy(), threads)
-    dt = time.perf_counter() - t0
-    parts["nn_%dq" % n2] = dt
-    t_total += dt * (B * 20 * Fb / n2)
-    # A4 forward: n4 points vs Fb faces, scaled to B*S (backward is O(S), negligible)
-    n4 = max(threads * 16, 512)
+    parts["A2 nearest neighbour, 1 sample full (%d x %d)" % (q.shape[1], S)] = dt = time.perf_counter() - t0
+    full["A2"] = dt * B
+    # ---- A4 forward: all S GT points of sample 0 vs its F_b faces (backward is O(S): negligible)
     t0 = time.perf_counter()
-    orc.point_face_distance(sc["gt"][:1, :n4].numpy(), faces.numpy(), None, threads)
-    dt = time.perf_counter() - t0
-    parts["face_dist_%dpts" % n4] = dt
-    t_total += dt * (B * S / n4)
-    # A5: full O(Fb^2) for one sample, times B
+    orc.point_face_distance(sc["gt"][:1].numpy(), faces.numpy(), None, threads)
+    parts["A4 point-face distance fwd, 1 sample full (%d x %d)" % (S, Fb)] = dt = time.perf_counter() - t0
+    full["A4"] = dt * B
+    # ---- A5: full O(F_b^2) for one sample
     t0 = time.perf_counter()
     orc.face_adjacency(faces[0].numpy(), 30, threads)
-    dt = time.perf_counter() - t0
-    parts["face_adj_1sample"] = dt
-    t_total += dt * B
-    desc = "oracle port on %d threads; bounded sample scaled to one full step (B=%d,T=%d,P=%d,S=%d,F_b=%d): %s" % (
-        threads, B, T, P, S, Fb, ", ".join("%s=%.3fs" % kv for kv in parts.items()))
-    return B * T / (t_total * 1e3), threads, desc
+    parts["A5 face adjacency, 1 sample full"] = dt = time.perf_counter() - t0
+    full["A5"] = dt * B
+    wall = time.perf_counter() - t_wall
+    est = float(sum(full.values()))
+    desc = ("%d host threads; measured: %s; full step estimated as energies + B x (A2 + A4 + A5 of one sample) + A1 scaled from %d to B x P "
+            "points = %.1f s (B=%d, T=%d, P=%d, S=%d, F_b=%d); energies: %s; A1/A2/A4/A5: oracle port of the reference's CUDA-only kernels "
+            "(the reference has no CPU implementation of them)" % (threads, "; ".join("%s = %.3f s" % kv for kv in parts.items()), n1, est, B, T, P, S,
+                                                                      Fb, energies_kind))
+    return {"value": B * T / (est * 1e3), "cores": threads, "desc": desc, "sample_wall_s": wall, "full_step_estimate_s": est,
+            "kind": "port (A1 extrapolated from %d points of one sample; A2/A4/A5 measured in full for one sample of %d; energies: %s)"
+                    % (n1, B, "reference class" if RefDefTet is not None else "port")}
 
 
 # ------------------------------------------------------------------------------------------------- reference CUDA leg
@@ -230,6 +290,85 @@ def reference_cuda_step(eng, grid, sc, Fmax, S_face, B, T):
             "boundary_faces_per_sample": [int(c) for c in counts_h]}
 
 
+# ------------------------------------------------------------------------------------------------- drop-in leg
+def dropin_step_leg(eng, grid, B, S, dev, steps=30):
+    """The number a DefTet user gets: the reference-shaped module call `DefTet.forward_surface_align` (occupancy labels by check_sign
+    against a watertight GT mesh, A9, A6-A8, A5, A3/A2, A4: layers/DefTet/deftet.py:51-130 as parallel.py:199-214 calls it) + the
+    loss arithmetic of train_multigpu.py:236-262 + backward, eager, timed with CUDA events; and GeometryEngine.losses (eager as well,
+    labels by the same check_sign call) on the SAME scene for comparison.  GT = one ellipsoid mesh per sample (icosphere level 5)."""
+    from deftet_b200 import render
+    from deftet_b200.deftet import DefTet
+    from deftet_b200.synthetic import icosphere
+    T, V = grid.n_tet, grid.n_vert
+    v_ico, f_ico = icosphere(5)
+    gen = torch.Generator().manual_seed(77)
+    base = torch.from_numpy(grid.centred())
+    mask = torch.from_numpy(grid.mask.astype(np.float32))
+    pos = (base.unsqueeze(0) + (torch.rand(B, V, 3, generator=gen) * 2 - 1) * (0.25 / grid.res) * mask).to(dev)
+    axes = 0.2 + 0.15 * torch.rand(B, 1, 3, generator=gen)
+    centre = (torch.rand(B, 1, 3, generator=gen) * 2 - 1) * 0.08
+    verts = [(torch.from_numpy(v_ico) * axes[b] + centre[b]).to(dev).unsqueeze(0) for b in range(B)]
+    faces = [torch.from_numpy(f_ico).to(dev).unsqueeze(0) for _ in range(B)]
+    d = torch.randn(B, S, 3, generator=gen)
+    gt = (d / d.norm(dim=-1, keepdim=True) * axes + centre).to(dev)
+    net = DefTet()
+    net.inverse_v = eng.inverse_v
+    tet64 = eng.tet.long()
+    f3, ft2 = eng.tet_face_fx3.long(), eng.tet_face_tetidx_fx2.long()
+    ex = lambda t: t.unsqueeze(0).expand(B, *([-1] * t.dim()))
+    delta = torch.zeros(V, 3, device=dev, requires_grad=True)
+    lam = dict(area=1e6, edge=1.0, surf=1.0, normal=0.1, amips=1.0, surf_chamfer=1.0)
+
+    def module_step():
+        delta.grad = None
+        out = net.forward_surface_align(pos + delta.unsqueeze(0), None, ex(tet64), [verts, faces], gt_surface_points=gt,
+                                        tet_face_bxfx3=ex(f3), tet_face_tet_bx4fx2=ex(ft2), inference=False)
+        amips, edge, area, surf, normal, center_occ, boundary, chamfer, lap_v = out
+        loss = (amips.mean() * lam["amips"] + edge.mean() * lam["edge"] + area.mean() * lam["area"] + surf.mean() * lam["surf"] +
+                normal.mean() * lam["normal"] + chamfer.mean() * lam["surf_chamfer"])
+        loss.backward()
+        return loss, center_occ
+
+    Fmax, S_face = eng.max_boundary_faces, eng.samples_per_face
+    gen_d = torch.Generator(device=dev).manual_seed(3)
+    u = torch.sqrt(torch.rand(B, Fmax, S_face, device=dev, generator=gen_d))
+    v = torch.rand(B, Fmax, S_face, device=dev, generator=gen_d)
+    vcat = torch.cat(verts)
+
+    def engine_step():
+        delta.grad = None
+        p = pos + delta.unsqueeze(0)
+        with torch.no_grad():
+            cen = p[:, eng.tet.long().reshape(-1)].reshape(B, -1, 4, 3).mean(dim=2)
+            occ = render.check_sign(vcat, faces[0][0], cen).float()
+        out = eng.losses(p, occ, gt, u, v, None, want=("energies", "chamfer", "distance", "normal"))
+        loss = (out["amips"].mean() * lam["amips"] + out["edge"].mean() * lam["edge"] + out["volume_variance"].mean() * lam["area"] +
+                out["distance"].mean() * lam["surf"] + out["normal"].mean() * lam["normal"] + out["chamfer"].mean() * lam["surf_chamfer"])
+        loss.backward()
+        return loss, occ
+
+    def timed(fn):
+        for _ in range(5):
+            l, occ = fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            l, occ = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps, float(l), occ
+
+    ms_mod, l_mod, occ_mod = timed(module_step)
+    ms_eng, l_eng, occ_eng = timed(engine_step)
+    return {"value": B * T / ms_mod, "unit": "tets/ms", "ms_per_step": ms_mod, "engine_same_scene_eager_ms": ms_eng,
+            "ratio_to_engine": ms_mod / ms_eng, "loss_module": l_mod, "loss_engine": l_eng,
+            "labels_identical": bool(torch.equal(occ_mod.reshape(B, -1), occ_eng.reshape(B, -1))),
+            "what": "deftet_b200.deftet.DefTet.forward_surface_align (labels by check_sign on a watertight GT mesh, boundary extraction, energies, "
+                    "normal / chamfer / surface-distance losses; no point-in-tet: training mode) + train_multigpu.py's loss sum + backward, "
+                    "eager; the chamfer samples differ between the two (the module draws its own torch.rand like the reference)"}
+
+
 # ------------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -249,6 +388,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--serial", action="store_true", help="enqueue the loss groups on one stream (profiling)")
     ap.add_argument("--skip-ref-cuda", action="store_true", help="do not time the reference's own CUDA kernels beside ours")
+    ap.add_argument("--skip-dropin", action="store_true", help="skip the leg through the reference-shaped DefTet module")
     ap.add_argument("--no-verify", action="store_true", help="skip the parity check of input set 0 against the reference's device kernels")
     args = ap.parse_args()
 
@@ -288,15 +428,18 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        vals = []
-        for k in range(max(1, min(args.steps, 3))):
-            v, cores, desc = cpu_reference_step(grid, B, P, S, 1000 * 3 + k)
-            vals.append(v)
-        v = float(np.median(vals))
+        # every step = ONE bounded sample of the workload (see cpu_reference_step); at most 3 are run so that the arm ends within
+        # minutes whatever --steps says, and `steps` reports how many were
+        n_rep = max(1, min(args.steps, 3))
+        runs = [cpu_reference_step(grid, B, P, S, 1000 * 3 + k) for k in range(n_rep)]
+        r = sorted(runs, key=lambda x: x["value"])[len(runs) // 2]
+        v = r["value"]
         line = {"impl": "reference", "metric": "tets/ms fwd+bwd (occ+AMIPS+chamfer) res-%d" % args.res, "value": v, "unit": "tets/ms",
-                "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": B * T / v, "higher_is_better": True,
+                "n_gpus": args.gpus, "steps": n_rep, "warmup": 0, "ms_per_step": r["sample_wall_s"] * 1e3, "higher_is_better": True,
                 "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": v, "unit": "tets/ms", "cores": cores, "kind": "port", "sample": desc},
+                "sample_is_bounded": True, "full_step_estimate_ms": r["full_step_estimate_s"] * 1e3,
+                "note": "ms_per_step is the MEASURED wall time of one bounded sample of the step; value = B*T / full_step_estimate_ms",
+                "cpu_baseline": {"value": v, "unit": "tets/ms", "cores": r["cores"], "kind": r["kind"], "sample": r["desc"]},
                 "e2e": {"value": v, "unit": "tets/ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return
@@ -444,8 +587,9 @@ def main():
         cpu = None
         if not args.skip_cpu:
             try:
-                v, cores, desc = cpu_reference_step(grid, B, P, S, 1000 * 3)
-                cpu = {"value": v, "unit": "tets/ms", "cores": cores, "kind": "port", "sample": desc}
+                r = cpu_reference_step(grid, B, P, S, 1000 * 3)
+                cpu = {"value": r["value"], "unit": "tets/ms", "cores": r["cores"], "kind": r["kind"], "sample": r["desc"],
+                       "sample_wall_s": r["sample_wall_s"], "full_step_estimate_s": r["full_step_estimate_s"]}
             except Exception as e:  # pragma: no cover
                 cpu = {"value": None, "unit": "tets/ms", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %s" % str(e)[:120]}
         parity = None
@@ -464,6 +608,12 @@ def main():
                     "against": "reference CUDA kernels (oracle/_ref/kernels_cuda, sm_100a build) + non-contracted C oracle, input set 0"}
             except Exception as e:  # pragma: no cover
                 parity = {"unavailable": "failed: %s" % str(e)[:200]}
+        dropin = None
+        if args.config == "3" and not args.skip_dropin:
+            try:
+                dropin = dropin_step_leg(eng, grid, B, S, dev)
+            except Exception as e:  # pragma: no cover
+                dropin = {"unavailable": "failed: %s" % str(e)[:200]}
         ref_cuda_leg = None
         if not args.skip_ref_cuda and world == 1:
             try:
@@ -476,7 +626,7 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "tets/ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "reference_cuda": ref_cuda_leg,
-                "parity": parity, "loss": loss_value}
+                "parity": parity, "e2e_dropin": dropin, "loss": loss_value}
         print(json.dumps(line))
 
 

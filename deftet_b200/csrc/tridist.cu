@@ -220,7 +220,8 @@ struct TriVisitor {
     }
 };
 
-// ---- query binning: the S points of each sample counting-sorted by the brick of the FACE grid they fall in ----
+// ---- query binning: the S points of each sample counting-sorted by the CELL of the FACE grid they fall in (brick-major cell order:
+// the queries of a brick stay contiguous, and 32 consecutive queries are spatially compact) ----
 __global__ void __launch_bounds__(256) qbin_count_kernel(const float* __restrict__ points, int S, int G, const unsigned* __restrict__ bbox_ord,
                                                          unsigned* __restrict__ qcount, unsigned* __restrict__ qbrick) {
     const int b = blockIdx.y;
@@ -228,9 +229,8 @@ __global__ void __launch_bounds__(256) qbin_count_kernel(const float* __restrict
     if (i >= S) return;
     GridParams g = grid_params(bbox_ord, b, G);
     const float* p = points + ((size_t)b * S + i) * 3;
-    const int NB = G >> 2;
-    int bx = cell_coord(p[0], g.ox, g.inv_h, G) >> 2, by = cell_coord(p[1], g.oy, g.inv_h, G) >> 2, bz = cell_coord(p[2], g.oz, g.inv_h, G) >> 2;
-    unsigned id = (unsigned)b * NB * NB * NB + ((unsigned)bz * NB + by) * NB + bx;
+    unsigned id = (unsigned)b * G * G * G +
+                  cell_index(cell_coord(p[0], g.ox, g.inv_h, G), cell_coord(p[1], g.oy, g.inv_h, G), cell_coord(p[2], g.oz, g.inv_h, G), G, true);
     qbrick[(size_t)b * S + i] = id;
     atomicAdd(qcount + id, 1u);
 }
@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
     __shared__ unsigned s_total;
     __shared__ unsigned s_n;
     __shared__ unsigned char s_rel[PFD_CHUNK];        // 1 = the centroid distance is a valid upper bound for this face
+    __shared__ unsigned char s_sub[WARPS][PFD_CHUNK]; // per warp: the staged candidates near this warp's 32 (cell-sorted, compact) queries
     __shared__ unsigned char s_list[PFD_THREADS][PFD_LIST];
     __shared__ float s_q[WARPS][32][3];               // the warp's queries (pooled evaluation reads other lanes' queries)
     __shared__ unsigned long long s_best[WARPS][32];  // (distance bits, face id): atomicMin == lexicographic minimum
@@ -294,8 +295,8 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
     const int NB = G >> 2;
     const int brick = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t qb = (size_t)b * NB * NB * NB + brick;
-    const unsigned q0 = qstart[qb], q1 = qend[qb];
+    const size_t qb = ((size_t)b * NB * NB * NB + brick) * 64;        // first cell of this brick (queries are sorted by cell)
+    const unsigned q0 = qstart[qb], q1 = qend[qb + 63];
     if (q0 == q1) return;
     const int nf = counts[b];
     const int na = n_always[b];
@@ -350,6 +351,15 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
             if (brute) { for (int f = 0; f < nf; ++f) v.face(f); }
         } else { v.p[0] = v.p[1] = v.p[2] = 0.f; }
         s_q[warp][lane][0] = v.p[0]; s_q[warp][lane][1] = v.p[1]; s_q[warp][lane][2] = v.p[2];
+        // The warp's 32 queries are neighbours (sorted by cell): only the staged faces whose centroid lies within `reach` of THEIR
+        // bounding box are scanned per query (the "sub-region"); a query is certified against everything outside of it below.
+        float slo[3], shi[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float lo = active ? v.p[k] : 3.0e38f, hi = active ? v.p[k] : -3.0e38f;
+            lo = warp_min(lo); hi = warp_max(hi);
+            slo[k] = fmaxf(lo - reach, rlo[k]); shi[k] = fminf(hi + reach, rhi[k]);
+        }
         float ub = 3.0e38f;                                 // upper bound of the answer: a centroid is a point of its face
         for (unsigned c0 = 0; c0 < total; c0 += PFD_SCAN) {
             // ---- stage (compacting): candidates c0 .. c0+PFD_SCAN of the 27 bricks that lie in the reach region ----
@@ -388,12 +398,28 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
                 }
             }
             __syncthreads();
-            const int n = (int)s_n;
+            const int n_staged = (int)s_n;
+            // ---- the warp's sub-list of the staged candidates ----
+            int n = 0;
+            for (int k0 = 0; k0 < n_staged; k0 += 32) {
+                const int k = k0 + lane;
+                bool in = false;
+                if (k < n_staged) {
+                    const float4 it = s_cen[k];
+                    in = it.x >= slo[0] && it.x <= shi[0] && it.y >= slo[1] && it.y <= shi[1] && it.z >= slo[2] && it.z <= shi[2];
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (in) s_sub[warp][n + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)k;
+                n += __popc(bal);
+            }
+            __syncwarp();
+            const unsigned char* sub = s_sub[warp];
             // ---- scan 1: upper bound from the centroid distances, and the nearest centroid ----
             int kn = -1;
             float dn = 3.0e38f;
             if (active) {
-                for (int k = 0; k < n; ++k) {
+                for (int i = 0; i < n; ++i) {
+                    const int k = sub[i];
                     float4 it = s_cen[k];
                     float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
                     float d2 = dx * dx + dy * dy + dz * dz;
@@ -415,7 +441,8 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
                 // the ball (centroid, radius)); the margins cover the rounding of this test, which only prunes and never decides
                 const float bound = fminf(ub * 1.0001f, v.best);
                 const float sb = sqrtf(bound) * 1.0002f;
-                for (int k = 0; k < n; ++k) {
+                for (int i = 0; i < n; ++i) {
+                    const int k = sub[i];
                     if (k == kn) continue;
                     float4 it = s_cen[k];
                     float dx = it.x - v.p[0], dy = it.y - v.p[1], dz = it.z - v.p[2];
@@ -489,14 +516,14 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
             }
         }
         if (active && !brute && nf > 0) {
-            // certify against faces that were not staged: their centroids lie outside the reach region (or outside the
-            // 3x3x3 bricks, which contain it); sides of the region beyond the face grid's bounding box hold no face
+            // certify against the faces that were not scanned: their centroids lie outside the warp's sub-region (which is inside the
+            // staged reach region, itself inside the 3x3x3 bricks); sides of it beyond the face grid's bounding box hold no face
             float db = 3.0e38f;
             const float o3[3] = {g.ox, g.oy, g.oz};
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                if (rlo[k] > o3[k]) db = fminf(db, v.p[k] - rlo[k]);
-                if (rhi[k] < o3[k] + gmax) db = fminf(db, rhi[k] - v.p[k]);
+                if (slo[k] > o3[k]) db = fminf(db, v.p[k] - slo[k]);
+                if (shi[k] < o3[k] + gmax) db = fminf(db, shi[k] - v.p[k]);
             }
             float lb = fmaxf(db - rmax - slack, 0.f) * 0.9999f;
             if (!(lb * lb > v.best))
@@ -625,7 +652,7 @@ __global__ void pfd_fill_none_kernel(float* __restrict__ d, float* __restrict__ 
 }
 
 extern "C" int dtb_point_face_distance_grid_res(int Fmax) {
-    int g = (int)ceil(sqrt((double)(Fmax > 1 ? Fmax : 1)) * 0.4375);
+    int g = (int)ceil(sqrt((double)(Fmax > 1 ? Fmax : 1)) * 0.375);      // res-70 sweep with cell-sorted queries (tools/r2_time.py a4): 48 at Fmax = 16384
     g = (g + 3) / 4 * 4;
     if (g < 4) g = 4;
     if (g > 128) g = 128;
@@ -634,7 +661,7 @@ extern "C" int dtb_point_face_distance_grid_res(int Fmax) {
 extern "C" size_t dtb_point_face_distance_workspace(int B, int S, int Fmax, int G) {
     if (G <= 0) G = dtb_point_face_distance_grid_res(Fmax);
     G = (G + 3) / 4 * 4;
-    size_t nbr = (size_t)B * (G / 4) * (G / 4) * (G / 4);
+    size_t nbr = (size_t)B * G * G * G;          // query bins: one per cell
     return pointgrid_workspace_bytes(B, Fmax, G, true, true) + align_up((size_t)B * PFD_ALWAYS_CAP * 4, 256) + 1024 +
            2 * align_up(nbr * 4, 256) + align_up((size_t)B * S * 4, 256) + align_up((size_t)B * S * 16, 256) + scan_workspace_bytes(nbr) + 256 +
            align_up((size_t)B * Fmax * 128, 256);
@@ -661,7 +688,7 @@ extern "C" int dtb_point_face_distance_forward(const float* points, const float*
     int32_t* always = ws.take<int32_t>((size_t)B * PFD_ALWAYS_CAP);
     unsigned* rmax = ws.take<unsigned>(B);
     int32_t* n_always = ws.take<int32_t>(B);
-    const size_t nbr = (size_t)B * (G / 4) * (G / 4) * (G / 4);
+    const size_t nbr = (size_t)B * G * G * G;    // query bins: one per cell of the face grid
     unsigned* qstart = ws.take<unsigned>(nbr);
     unsigned* qend = ws.take<unsigned>(nbr);
     unsigned* qbrick = ws.take<unsigned>((size_t)B * S);

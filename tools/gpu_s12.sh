@@ -1,0 +1,6 @@
+#!/bin/sh
+OUT=gpurun_out
+mkdir -p $OUT
+timeout 900 python -m pytest tests/test_gpu_search.py tests/test_gpu_robustness.py tests/test_gpu_reference_cuda.py tests/test_gpu_scale_parity.py tests/test_gpu_golden.py tests/test_gpu_dropin.py -q -x > $OUT/s12_tests.log 2>&1; echo "pytest rc=$?" >> $OUT/s12_tests.log
+tail -5 $OUT/s12_tests.log | cut -c1-300
+timeout 300 python tools/r2_time.py pit a4 > $OUT/s12_time.jsonl 2> $OUT/s12_time.err; cut -c1-200 $OUT/s12_time.jsonl
