@@ -55,10 +55,12 @@ __global__ void cs_init_kernel(unsigned* bbox_ord, int B) {
 // pass 0: count (cell, tri) pairs per cell; pass 1: fill
 __global__ void __launch_bounds__(256) cs_bin_kernel(const float* __restrict__ verts, int n, const int32_t* __restrict__ faces, int m, int R,
                                                      const unsigned* __restrict__ bbox_ord, unsigned* __restrict__ cell_cnt,
-                                                     unsigned* __restrict__ cell_cur, int32_t* __restrict__ cell_list, int pass) {
+                                                     unsigned* __restrict__ cell_cur, int32_t* __restrict__ cell_list, int pass,
+                                                     const unsigned* __restrict__ total = nullptr, size_t cap = 0) {
     int b = blockIdx.y;
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= m) return;
+    if (pass == 1 && total && (size_t)*total > cap) return;          // list would overflow: the query falls back to all faces
     XYGrid g = xy_grid(bbox_ord, b, R);
     const float* vb = verts + (size_t)b * n * 3;
     int i0 = faces[f * 3], i1 = faces[f * 3 + 1], i2 = faces[f * 3 + 2];
@@ -89,7 +91,8 @@ __device__ __forceinline__ bool edge_inside(double ax, double ay, double bx, dou
 __global__ void __launch_bounds__(256) cs_query_kernel(const float* __restrict__ verts, int n, const int32_t* __restrict__ faces, int R,
                                                        const unsigned* __restrict__ bbox_ord, const unsigned* __restrict__ cell_start,
                                                        const unsigned* __restrict__ cell_end, const int32_t* __restrict__ cell_list,
-                                                       const float* __restrict__ points, int p, unsigned char* __restrict__ out) {
+                                                       const float* __restrict__ points, int p, unsigned char* __restrict__ out,
+                                                       int m = 0, const unsigned* __restrict__ total = nullptr, size_t cap = 0) {
     int b = blockIdx.y;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p) return;
@@ -102,20 +105,24 @@ __global__ void __launch_bounds__(256) cs_query_kernel(const float* __restrict__
         size_t c = ((size_t)b * R + xy_cell(py, g.oy, g.inv, R)) * R + xy_cell(px, g.ox, g.inv, R);
         const float* vb = verts + (size_t)b * n * 3;
         unsigned crossings = 0;
-        for (unsigned j = cell_start[c]; j < cell_end[c]; ++j) {
-            int f = cell_list[j];
+        auto crosses = [&](int f) -> bool {
             const float* A = vb + (size_t)faces[f * 3] * 3; const float* Bv = vb + (size_t)faces[f * 3 + 1] * 3; const float* Cv = vb + (size_t)faces[f * 3 + 2] * 3;
             double ax = A[0], ay = A[1], bx = Bv[0], by = Bv[1], cx = Cv[0], cy = Cv[1];
             double area = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
-            if (area == 0.0) continue;                               // projects to a segment: never crossed
+            if (area == 0.0) return false;                           // projects to a segment: never crossed
             bool ccw = area > 0.0;
             if (!edge_inside(ax, ay, bx, by, px, py, ccw) || !edge_inside(bx, by, cx, cy, px, py, ccw) || !edge_inside(cx, cy, ax, ay, px, py, ccw))
-                continue;
+                return false;
             // z of the triangle's plane at (px, py)
             double w0 = ((bx - px) * (cy - py) - (by - py) * (cx - px)) / area;
             double w1 = ((cx - px) * (ay - py) - (cy - py) * (ax - px)) / area;
             double z = w0 * (double)A[2] + w1 * (double)Bv[2] + (1.0 - w0 - w1) * (double)Cv[2];
-            if (z > pz) ++crossings;
+            return z > pz;
+        };
+        if (total && (size_t)*total > cap) {                         // the (cell, triangle) list did not fit: every face (same answer)
+            for (int f = 0; f < m; ++f) crossings += crosses(f) ? 1u : 0u;
+        } else {
+            for (unsigned j = cell_start[c]; j < cell_end[c]; ++j) crossings += crosses(cell_list[j]) ? 1u : 0u;
         }
         inside = (crossings & 1u) != 0u;
     }
@@ -187,16 +194,17 @@ extern "C" size_t dtb_check_sign_workspace(int B, int m, int R) {
 }
 // verts (B,n,3) f32, faces (m,3) i32 shared by the batch, points (B,p,3) f32 -> out (B,p) u8 (1 = inside).
 // R = cells per axis of the xy hash grid (kaolin's hash_resolution; <= 0 -> 256).
-extern "C" int dtb_check_sign(const float* verts, const int32_t* faces, const float* points, int B, int n, int m, int p, int R,
-                              unsigned char* out, void* workspace, size_t workspace_bytes, void* stream) {
-    if (p == 0 || B == 0) return DTB_OK;
-    DTB_REQUIRE(points && out, "check_sign: null argument");
+static int check_sign_impl(const float* verts, const int32_t* faces, const float* points, int B, int n, int m, int p, int R, bool fixed,
+                           int* r_used, unsigned char* out, void* workspace, size_t workspace_bytes, void* stream) {
+    if ((p == 0 && !r_used) || B == 0) return DTB_OK;
+    DTB_REQUIRE((points && out) || p == 0, "check_sign: null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    if (m == 0 || n == 0) { DTB_CUDA(cudaMemsetAsync(out, 0, (size_t)B * p, st)); return DTB_OK; }
+    if (m == 0 || n == 0) { if (p) DTB_CUDA(cudaMemsetAsync(out, 0, (size_t)B * p, st)); if (r_used) *r_used = R; return DTB_OK; }
     DTB_REQUIRE(verts && faces, "check_sign: null mesh");
     if (R <= 0) R = 256;
     if (R > 1024) R = 1024;
-    size_t cells = (size_t)B * R * R;
+    const int R_ws = R;                                   // the workspace was sized for this resolution (only ever shrinks below)
+    size_t cells = (size_t)B * R_ws * R_ws;
     Workspace ws(workspace, workspace_bytes);
     unsigned* bbox = ws.take<unsigned>((size_t)B * 6);
     unsigned* cstart = ws.take<unsigned>(cells);
@@ -212,8 +220,9 @@ extern "C" int dtb_check_sign(const float* verts, const int32_t* faces, const fl
     cs_bbox_kernel<<<gv, 256, 0, st>>>(verts, n, bbox);
     DTB_LAUNCH_CHECK("cs_bbox");
     dim3 gf(cdiv(m, 256), B);
-    // the (cell, triangle) list has a fixed capacity: halve the grid resolution until it fits (setup-time op, one small
-    // blocking copy per attempt)
+    // the (cell, triangle) list has a fixed capacity.  Blocking form: halve the grid resolution until it fits (one small blocking
+    // copy per attempt).  Fixed form (a resolution found earlier for a mesh of this size): never synchronises -- should the list
+    // overflow after all, the fill is skipped on the device and the query tests every face instead (same answer, slower).
     for (;;) {
         cells = (size_t)B * R * R;
         DTB_CUDA(cudaMemsetAsync(cstart, 0, cells * 4, st));
@@ -221,6 +230,7 @@ extern "C" int dtb_check_sign(const float* verts, const int32_t* faces, const fl
         DTB_LAUNCH_CHECK("cs_bin_count");
         int rc = exclusive_scan_u32(cstart, cstart, cells, total, sws, sb, st);
         if (rc) return rc;
+        if (fixed) break;
         unsigned h_total = 0;
         DTB_CUDA(cudaMemcpyAsync(&h_total, total, 4, cudaMemcpyDeviceToHost, st));
         DTB_CUDA(cudaStreamSynchronize(st));
@@ -228,13 +238,32 @@ extern "C" int dtb_check_sign(const float* verts, const int32_t* faces, const fl
         if (R <= 1) { set_error("check_sign: %u (cell, triangle) pairs exceed the workspace capacity %zu", h_total, cap); return DTB_EOVERFLOW; }
         R = R > 2 ? R / 2 : 1;
     }
+    if (r_used) *r_used = R;
+    if (p == 0) return DTB_OK;
     DTB_CUDA(cudaMemcpyAsync(cend, cstart, cells * 4, cudaMemcpyDeviceToDevice, st));
-    cs_bin_kernel<<<gf, 256, 0, st>>>(verts, n, faces, m, R, bbox, nullptr, cend, list, 1);
+    cs_bin_kernel<<<gf, 256, 0, st>>>(verts, n, faces, m, R, bbox, nullptr, cend, list, 1, total, cap);
     DTB_LAUNCH_CHECK("cs_bin_fill");
     dim3 gp(cdiv(p, 256), B);
-    cs_query_kernel<<<gp, 256, 0, st>>>(verts, n, faces, R, bbox, cstart, cend, list, points, p, out);
+    cs_query_kernel<<<gp, 256, 0, st>>>(verts, n, faces, R, bbox, cstart, cend, list, points, p, out, m, total, cap);
     DTB_LAUNCH_CHECK("cs_query");
+    (void)R_ws;
     return DTB_OK;
+}
+
+extern "C" int dtb_check_sign(const float* verts, const int32_t* faces, const float* points, int B, int n, int m, int p, int R,
+                              unsigned char* out, void* workspace, size_t workspace_bytes, void* stream) {
+    return check_sign_impl(verts, faces, points, B, n, m, p, R, false, nullptr, out, workspace, workspace_bytes, stream);
+}
+// Same, and reports the grid resolution that was finally used (<= R): feed it to dtb_check_sign_fixed for later meshes of this size.
+extern "C" int dtb_check_sign_probe(const float* verts, const int32_t* faces, const float* points, int B, int n, int m, int p, int R,
+                                    unsigned char* out, int* r_used, void* workspace, size_t workspace_bytes, void* stream) {
+    DTB_REQUIRE(r_used, "check_sign_probe: null r_used");
+    return check_sign_impl(verts, faces, points, B, n, m, p, R, false, r_used, out, workspace, workspace_bytes, stream);
+}
+// Non-blocking form: resolution R as given, no host synchronisation (capturable); a list overflow is handled on the device.
+extern "C" int dtb_check_sign_fixed(const float* verts, const int32_t* faces, const float* points, int B, int n, int m, int p, int R,
+                                    unsigned char* out, void* workspace, size_t workspace_bytes, void* stream) {
+    return check_sign_impl(verts, faces, points, B, n, m, p, R, true, nullptr, out, workspace, workspace_bytes, stream);
 }
 
 // A17.  d (B,V,3) offsets; edges (E,2) i32 sorted by first column with weight (E,) from dtb_tet_point_adj.

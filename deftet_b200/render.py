@@ -29,6 +29,8 @@ def _render_sigs(lib, sig):
     sig("dtb_render_composite_backward", i, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, f, i, ll, vp, vp, vp, sz, vp)
     sig("dtb_check_sign_workspace", sz, i, i, i)
     sig("dtb_check_sign", i, vp, vp, vp, i, i, i, i, i, vp, vp, sz, vp)
+    sig("dtb_check_sign_probe", i, vp, vp, vp, i, i, i, i, i, vp, vp, vp, sz, vp)
+    sig("dtb_check_sign_fixed", i, vp, vp, vp, i, i, i, i, i, vp, vp, sz, vp)
     sig("dtb_laplacian_forward", i, vp, vp, vp, i, i, i, vp, vp, vp, vp, vp)
     sig("dtb_laplacian_backward", i, vp, vp, vp, vp, vp, i, i, vp, vp)
 
@@ -151,8 +153,15 @@ def render_composite(pixel_coords, render_ranges, face_vertices_z, face_vertices
                                   int(grid_res))
 
 
+_CS_RES = {}           # (n_verts, n_faces, hash_resolution) -> grid resolution that fitted the first mesh of that size
+
+
 def check_sign(verts, faces, points, hash_resolution=512):
-    """verts (B,n,3), faces (m,3) long, points (B,p,3) -> bool (B,p): True where the point is inside the mesh."""
+    """verts (B,n,3), faces (m,3) long, points (B,p,3) -> bool (B,p): True where the point is inside the mesh.
+
+    The first call for a mesh size finds a grid resolution whose (cell, triangle) list fits (blocking, set-up time); later calls
+    with meshes of that size reuse it without any host synchronisation (the training loop labels B samples per step,
+    layers/DefTet/deftet.py:33-49) -- a mesh that overflows after all is answered by testing every face on the device."""
     _lib.require_cuda(verts, faces, points)
     v, p = _f32c(verts), _f32c(points)
     f = faces.to(torch.int32).contiguous()
@@ -163,9 +172,16 @@ def check_sign(verts, faces, points, hash_resolution=512):
     R = min(int(hash_resolution), 1024)
     wsz = L.dtb_check_sign_workspace(B, m, R)
     ws = torch.empty(wsz, device=dev, dtype=torch.uint8)
+    key = (n, m, R)
     with torch.cuda.device(dev):
-        _lib.check(L.dtb_check_sign(_lib.ptr(v), _lib.ptr(f), _lib.ptr(p), B, n, m, npts, R, _lib.ptr(out), _lib.ptr(ws), wsz,
-                                    _lib.stream_ptr()), "dtb_check_sign")
+        if key in _CS_RES:
+            _lib.check(L.dtb_check_sign_fixed(_lib.ptr(v), _lib.ptr(f), _lib.ptr(p), B, n, m, npts, _CS_RES[key], _lib.ptr(out), _lib.ptr(ws), wsz,
+                                              _lib.stream_ptr()), "dtb_check_sign_fixed")
+        else:
+            r_used = C.c_int(0)
+            _lib.check(L.dtb_check_sign_probe(_lib.ptr(v), _lib.ptr(f), _lib.ptr(p), B, n, m, npts, R, _lib.ptr(out), C.byref(r_used), _lib.ptr(ws),
+                                              wsz, _lib.stream_ptr()), "dtb_check_sign_probe")
+            _CS_RES[key] = int(r_used.value)
     return out.bool()
 
 

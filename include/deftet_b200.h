@@ -284,6 +284,13 @@ int dtb_render_composite_backward(const float* pixel_coords, const float* render
 size_t dtb_check_sign_workspace(int B, int m, int R);
 int dtb_check_sign(const float* verts, const int32_t* faces, const float* points, int B, int n, int m, int p, int R,
                    unsigned char* out, void* workspace, size_t workspace_bytes, void* stream);
+/* dtb_check_sign + the grid resolution finally used (<= R) in *r_used: blocking like dtb_check_sign (set-up time). */
+int dtb_check_sign_probe(const float* verts, const int32_t* faces, const float* points, int B, int n, int m, int p, int R,
+                         unsigned char* out, int* r_used, void* workspace, size_t workspace_bytes, void* stream);
+/* Non-blocking dtb_check_sign at a resolution found earlier (dtb_check_sign_probe) for a mesh of this size: no host
+ * synchronisation, capturable in a CUDA graph; if the (cell, triangle) list overflows the query tests every face on the device. */
+int dtb_check_sign_fixed(const float* verts, const int32_t* faces, const float* points, int B, int n, int m, int p, int R,
+                         unsigned char* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- A17: Laplacian smoothness sum ||(D^-1 A) d - d||^2 (layers/DefTet/deftet.py:340-343) -------------------
  * d (B,V,3); edges (E,2) + weight (E,) from dtb_tet_point_adj (sorted by row).  resid_ws (B,V,3) and rows_ws (V+1)
