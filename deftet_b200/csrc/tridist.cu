@@ -264,6 +264,11 @@ constexpr int PFD_THREADS = PFD_THREADS_N;
 #ifndef PFD_CHUNK_N
 #define PFD_CHUNK_N 128
 #endif
+#ifndef PFD_SCAN_UNROLL
+#define PFD_SCAN_UNROLL 1
+#endif
+#define DTB_PRAGMA_(x) _Pragma(#x)
+#define DTB_UNROLL(n) DTB_PRAGMA_(unroll n)
 #ifndef PFD_PLANE_PRUNE
 #define PFD_PLANE_PRUNE 1            // scan 2 also rejects faces whose PLANE is farther than the bound (A/B: -8 % on the op, bit-identical)
 #endif
@@ -418,6 +423,7 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
             int kn = -1;
             float dn = 3.0e38f;
             if (active) {
+DTB_UNROLL(PFD_SCAN_UNROLL)
                 for (int i = 0; i < n; ++i) {
                     const int k = sub[i];
                     float4 it = s_cen[k];
@@ -441,6 +447,7 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
                 // the ball (centroid, radius)); the margins cover the rounding of this test, which only prunes and never decides
                 const float bound = fminf(ub * 1.0001f, v.best);
                 const float sb = sqrtf(bound) * 1.0002f;
+DTB_UNROLL(PFD_SCAN_UNROLL)
                 for (int i = 0; i < n; ++i) {
                     const int k = sub[i];
                     if (k == kn) continue;
