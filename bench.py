@@ -385,6 +385,9 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU (weak scaling)")
     ap.add_argument("--points", type=int, default=100000)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--shapes", default="1,3", help="ellipsoids per sample lo,hi (SURVEY.md 8d: 1-3; 40,48 gives ~12 k boundary faces per sample, "
+                                                    "the 'ShapeNet is 2-4x' end of the workload)")
+    ap.add_argument("--load-steps", type=int, default=LOAD_STEPS, help="untimed steps before the timed region while nvidia-smi samples the clocks")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--serial", action="store_true", help="enqueue the loss groups on one stream (profiling)")
     ap.add_argument("--skip-ref-cuda", action="store_true", help="do not time the reference's own CUDA kernels beside ours")
@@ -453,10 +456,13 @@ def main():
         # a mismatched collective must fail within minutes, not after NCCL's 10-minute watchdog (round-1 N=2 hang)
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=PG_TIMEOUT_S))
     from deftet_b200.engine import GeometryEngine
-    Fmax, S_face = 16384, 20
+    shapes = tuple(int(x) for x in args.shapes.split(","))
+    Fmax, S_face = (16384 if shapes[1] <= 3 else 32768), 20
     eng = GeometryEngine(grid.centred(), grid.tets, max_boundary_faces=Fmax, samples_per_face=S_face, device=dev)
     NSETS = 4          # inputs rotate over NSETS sets (> L2 together) so that no step finds its inputs in L2
-    scenes = [analytic_scene(grid, B, P, S, 1000 * 3 + 17 * rank + s, dev) for s in range(NSETS)]
+    scenes = [analytic_scene(grid, B, P, S, 1000 * 3 + 17 * rank + s, dev, shapes=shapes) for s in range(NSETS)]
+    if shapes != (1, 3):
+        config["shapes_per_sample"] = list(shapes)
     gen = torch.Generator(device=dev).manual_seed(7 + rank)
     uv = [(torch.sqrt(torch.rand(B, Fmax, S_face, device=dev, generator=gen)), torch.rand(B, Fmax, S_face, device=dev, generator=gen))
           for _ in range(NSETS)]
@@ -477,6 +483,8 @@ def main():
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     assert int(ovf.item()) == 0, "boundary face capacity exceeded"
+    if counts is not None:
+        config["boundary_faces_per_sample"] = [int(c) for c in counts.tolist()]          # of the last warm-up input set
     graphs = None
     if not args.no_graph:
         try:
@@ -511,7 +519,7 @@ def main():
         dist.barrier()
     # Keep the GPU under the same load while nvidia-smi collects samples.  The count is FIXED: every rank must issue the
     # same number of all-reduces (a wall-clock bound gave each rank a different count and dead-locked N=2 in round 1).
-    for w in range(LOAD_STEPS + args.warmup):
+    for w in range(args.load_steps + args.warmup):
         run(w)
     torch.cuda.synchronize()
     if world > 1:
@@ -533,8 +541,12 @@ def main():
     value = world * B * T / ms_per_step
 
     # ---- e2e: host buffers in, losses + gradient out, through the same public call ------------------------
-    host = [{k: v.cpu().pin_memory() for k, v in sc.items()} for sc in scenes]
-    h2d = sum(v.numel() * 4 for v in host[0].values())
+    # {0,1}-valued inputs (tet occupancy labels, point labels, vertex labels) travel as uint8 and are widened on the device (a data
+    # loader would ship them like that; round 1 sent them as fp32 and the host side saturated at 8 GPUs)
+    U8 = ("occ", "target", "vfield")
+    host = [{k: (v.to(torch.uint8) if k in U8 else v).cpu().pin_memory() for k, v in sc.items()} for sc in scenes]
+    stage = [{k: torch.empty_like(scenes[s][k], dtype=torch.uint8) for k in U8} for s in range(NSETS)]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
     out_loss = torch.empty((), dtype=torch.float32).pin_memory()
     out_grad = torch.empty(V, 3, dtype=torch.float32).pin_memory()
     d2h = out_loss.numel() * 4 + out_grad.numel() * 4
@@ -546,7 +558,11 @@ def main():
         """H2D of step k's inputs from pinned memory into input set k % NSETS (its previous reader has completed)."""
         with torch.cuda.stream(copy_stream):
             for name, t in host[k % NSETS].items():
-                scenes[k % NSETS][name].copy_(t, non_blocking=True)
+                if name in U8:
+                    stage[k % NSETS][name].copy_(t, non_blocking=True)
+                    scenes[k % NSETS][name].copy_(stage[k % NSETS][name])          # widen to the fp32 the kernels read
+                else:
+                    scenes[k % NSETS][name].copy_(t, non_blocking=True)
             ready[k % NSETS].record(copy_stream)
 
     def run_e2e(k):
@@ -723,12 +739,13 @@ def roofline_pass(eng, step, scenes, uv, B, T, V, P, S, Fmax, S_face, NSETS, ite
     L = _lib.lib()
     L.dtb_profile_enable.argtypes = [ctypes.c_int]
     L.dtb_profile_elapsed.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
-    tags = ["energies_fwd_kernel", "energies_bwd_kernel", "pit_tet_kernel", "nn_query_thread_kernel", "pfd_forward_tiled_kernel",
+    tags = ["energies_fwd_kernel", "energies_bwd_kernel", "pit_tet_kernel", "nn_query_group_kernel", "pfd_forward_tiled_kernel",
             "bary_backward_kernel"]
     Q = 20 * Fb
-    kbytes = {"energies_fwd_kernel": 52 * T + 12 * B * V + 4 * B * T, "energies_bwd_kernel": 52 * T + 12 * B * V + 12 * B * V,
-              "pit_tet_kernel": 16 * T + 12 * B * V + 16 * B * P + 4 * B * P, "nn_query_thread_kernel": B * (16 * Q + 16 * S + 4 * Q),
-              "pfd_forward_tiled_kernel": B * (16 * S + 36 * Fb + 16 * Fb + 8 * S), "bary_backward_kernel": B * (12 * P + 4 * P + 16 * P) + 12 * B * V + 12 * B * V}
+    # algorithmic bytes per launch, SURVEY.md 8(d): unique bytes that must cross HBM once (fp32 coordinates, int32 indices)
+    kbytes = {"energies_fwd_kernel": 52 * T + 12 * B * V, "energies_bwd_kernel": 52 * T + 12 * B * V + 12 * B * V,
+              "pit_tet_kernel": B * (12 * P + 4 * P + 16 * P) + 12 * B * V + 16 * T, "nn_query_group_kernel": B * (12 * Q + 12 * S + 4 * Q),
+              "pfd_forward_tiled_kernel": B * (12 * S + 36 * Fb + 8 * S), "bary_backward_kernel": B * (16 * P + 12 * P) + 12 * B * V}
     acc = {t: [] for t in tags}
     L.dtb_profile_enable(1)
     for k in range(6):
@@ -755,14 +772,14 @@ def roofline_pass(eng, step, scenes, uv, B, T, V, P, S, Fmax, S_face, NSETS, ite
             "kernels_frac": {k: round(kbytes[k] / (v * 1e-3) / 1e9 / peak, 4) for k, v in kms.items()},
             "groups_ms": {k: round(v[0], 4) for k, v in groups.items()},
             "groups_frac": {k: round(v[1] / (v[0] * 1e-3) / 1e9 / peak, 4) for k, v in groups.items()},
-            "note": "search kernels are instruction/latency bound (exact-semantics fp32 predicates on binned candidates): DRAM traffic is "
-                    "1-3 % of peak in the ncu captures (profiles/), sm_throughput_pct_ncu is the SM pipe utilisation of the same capture; "
-                    "algorithmic bytes per DESIGN.md section 4"}
+            "note": "the search kernels are instruction-issue bound (130-145 M warp instructions per launch at 57-68 % issue utilisation, "
+                    "profiles/r2_ncu_full_search_kernels.md); their DRAM traffic equals the algorithmic bytes (ratio ~1.0), so the HBM fraction is "
+                    "small by construction; sm_throughput_pct_ncu is the SM pipe utilisation of the ncu capture; algorithmic bytes per SURVEY.md 8(d)"}
     try:
         # secondary figure for the search kernels: flops of the reference's brute-force formulation / this kernel's time,
         # next to the FP32 peak of the chip (148 SMs x 128 lanes x 2 flop x boost clock) -- how far the binning + pruning beats a
         # speed-of-light all-pairs kernel, since the HBM fraction says little about an ALU-bound search
-        bf = {"pit_tet_kernel": 60.0 * B * P * T, "nn_query_thread_kernel": 8.0 * B * Q * S, "pfd_forward_tiled_kernel": 120.0 * B * S * Fb}
+        bf = {"pit_tet_kernel": 60.0 * B * P * T, "nn_query_group_kernel": 8.0 * B * Q * S, "pfd_forward_tiled_kernel": 120.0 * B * S * Fb}
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
         roof["fp32_peak_tflops_nominal"] = round(fp32_peak, 1)
         roof["brute_force_equivalent"] = {k: {"reference_flops": v, "tflops_equivalent": round(v / (kms[k] * 1e-3) / 1e12, 1),

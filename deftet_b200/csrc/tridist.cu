@@ -265,7 +265,7 @@ constexpr int PFD_THREADS = PFD_THREADS_N;
 #define PFD_CHUNK_N 128
 #endif
 #ifndef PFD_SCAN_UNROLL
-#define PFD_SCAN_UNROLL 1
+#define PFD_SCAN_UNROLL 4          // A/B on the surface-distance op (res 70 b8): 1 -> 0.339, 2 -> 0.341, 4 -> 0.328 ms
 #endif
 #define DTB_PRAGMA_(x) _Pragma(#x)
 #define DTB_UNROLL(n) DTB_PRAGMA_(unroll n)
