@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
     // grid (rmax + 1.25 h > one brick; found by the res-40 scale parity test, where a small shape gives a fine grid) it is clamped
     // to them, and the queries whose ball leaves the clamped region take the general walk.
     const float reach = fminf(rmax + PFD_REACH_H * g.h, bw);
+    const float margin = fmaxf(reach - rmax, 0.f);          // = PFD_REACH_H cells unless the reach was clamped
     const float lx0 = g.ox + (float)bx0 * bw, ly0 = g.oy + (float)by0 * bw, lz0 = g.oz + (float)bz0 * bw;
     const float rlo[3] = {lx0 - reach, ly0 - reach, lz0 - reach}, rhi[3] = {lx0 + bw + reach, ly0 + bw + reach, lz0 + bw + reach};
     const float gmax = (float)G * g.h;
@@ -356,14 +357,15 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
             if (brute) { for (int f = 0; f < nf; ++f) v.face(f); }
         } else { v.p[0] = v.p[1] = v.p[2] = 0.f; }
         s_q[warp][lane][0] = v.p[0]; s_q[warp][lane][1] = v.p[1]; s_q[warp][lane][2] = v.p[2];
-        // The warp's 32 queries are neighbours (sorted by cell): only the staged faces whose centroid lies within `reach` of THEIR
-        // bounding box are scanned per query (the "sub-region"); a query is certified against everything outside of it below.
-        float slo[3], shi[3];
+        // The warp's 32 queries are neighbours (sorted by cell): per query only those staged faces are scanned whose bounding sphere
+        // (centroid, the face's OWN radius) comes within `margin` of the queries' bounding box.  A staged face that is left out is
+        // farther than `margin` from every query of the warp, so a query whose best distance is below `margin` needs none of them
+        // (certified below, together with the faces that were not staged at all).
+        float wlo[3], whi[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             float lo = active ? v.p[k] : 3.0e38f, hi = active ? v.p[k] : -3.0e38f;
-            lo = warp_min(lo); hi = warp_max(hi);
-            slo[k] = fmaxf(lo - reach, rlo[k]); shi[k] = fminf(hi + reach, rhi[k]);
+            wlo[k] = warp_min(lo); whi[k] = warp_max(hi);
         }
         float ub = 3.0e38f;                                 // upper bound of the answer: a centroid is a point of its face
         for (unsigned c0 = 0; c0 < total; c0 += PFD_SCAN) {
@@ -411,7 +413,10 @@ __global__ void __launch_bounds__(PFD_THREADS, PFD_MIN_CTAS) pfd_forward_tiled_k
                 bool in = false;
                 if (k < n_staged) {
                     const float4 it = s_cen[k];
-                    in = it.x >= slo[0] && it.x <= shi[0] && it.y >= slo[1] && it.y <= shi[1] && it.z >= slo[2] && it.z <= shi[2];
+                    const float dx = fmaxf(fmaxf(wlo[0] - it.x, it.x - whi[0]), 0.f), dy = fmaxf(fmaxf(wlo[1] - it.y, it.y - whi[1]), 0.f);
+                    const float dz = fmaxf(fmaxf(wlo[2] - it.z, it.z - whi[2]), 0.f);
+                    const float rr = fminf(s_pre[(size_t)k * FACEPRE_STRIDE + (FACEPRE_FLOATS - 1)], rmax) + margin;      // own radius (inflated)
+                    in = !(dx * dx + dy * dy + dz * dz > rr * rr * 1.0002f);          // conservative inclusion (NaN: included)
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, in);
                 if (in) s_sub[warp][n + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)k;
@@ -523,17 +528,19 @@ DTB_UNROLL(PFD_SCAN_UNROLL)
             }
         }
         if (active && !brute && nf > 0) {
-            // certify against the faces that were not scanned: their centroids lie outside the warp's sub-region (which is inside the
-            // staged reach region, itself inside the 3x3x3 bricks); sides of it beyond the face grid's bounding box hold no face
+            // certify against the faces that were not scanned.  (i) not staged: their centroids lie outside the staged reach region
+            // (inside the 3x3x3 bricks); sides of it beyond the face grid's bounding box hold no face.  (ii) staged but not on the
+            // warp's sub-list: farther than `margin` from every query of the warp.
             float db = 3.0e38f;
             const float o3[3] = {g.ox, g.oy, g.oz};
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                if (slo[k] > o3[k]) db = fminf(db, v.p[k] - slo[k]);
-                if (shi[k] < o3[k] + gmax) db = fminf(db, shi[k] - v.p[k]);
+                if (rlo[k] > o3[k]) db = fminf(db, v.p[k] - rlo[k]);
+                if (rhi[k] < o3[k] + gmax) db = fminf(db, rhi[k] - v.p[k]);
             }
             float lb = fmaxf(db - rmax - slack, 0.f) * 0.9999f;
-            if (!(lb * lb > v.best))
+            const float lm = margin * 0.999f;
+            if (!(lb * lb > v.best) || !(lm * lm > v.best))
                 brick_walk(v.p[0], v.p[1], v.p[2], g, G, rmax, cell_start, cell_end, sorted, mask, cell_base, v);
         }
         if (active) {
