@@ -69,8 +69,11 @@ struct PitSoup {
 #ifndef PIT_UNROLL
 #define PIT_UNROLL 1
 #endif
+#ifndef PIT_MIN_CTAS
+#define PIT_MIN_CTAS 1
+#endif
 template <typename Src>
-__global__ void __launch_bounds__(128) pit_tet_kernel(Src src, int T, int P, int G, const unsigned* __restrict__ bbox_ord,
+__global__ void __launch_bounds__(128, PIT_MIN_CTAS) pit_tet_kernel(Src src, int T, int P, int G, const unsigned* __restrict__ bbox_ord,
                                                       const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_end,
                                                       const float4* __restrict__ sorted, int* __restrict__ hit, int* __restrict__ weak_list,
                                                       int* __restrict__ n_weak) {
@@ -361,6 +364,9 @@ __global__ void __launch_bounds__(128) nn_query_thread_kernel(const float* __res
 //            from the minimum found so far.
 // Result = lexicographic minimum of (distance, index) over a superset of every point that can attain the minimum: identical
 // to the brute-force scan of nearest_neighbor_cuda.cu:17-55.
+#ifndef NN_DENSE
+#define NN_DENSE 0
+#endif
 #ifndef NN_COOP_RCAP
 #define NN_COOP_RCAP 2.0f
 #endif
@@ -473,12 +479,22 @@ __global__ void __launch_bounds__(128) nn_query_group_kernel(const float* __rest
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+#if NN_DENSE
+    // 32 CONSECUTIVE queries per warp whatever the group size (a face's 20 samples leave 12 lanes idle otherwise): consecutive
+    // boundary faces come from neighbouring tets, so the warp still covers one compact patch
+    const long long nq = (long long)q_counts[b] * q_mult;
+    const long long i0 = (long long)w * 32;
+    if (i0 >= nq) return;                                     // warp-uniform
+    const bool active = i0 + lane < nq;
+    const size_t qi = (size_t)b * Q + (size_t)(active ? i0 + lane : i0);
+#else
     const int cpg = (q_mult + 31) >> 5;                       // chunks per group
     const int group = w / cpg, chunk = w - group * cpg;
     if (group >= q_counts[b]) return;                         // warp-uniform
     const int l0 = chunk * 32;
     const bool active = l0 + lane < q_mult;
     const size_t qi = (size_t)b * Q + (size_t)group * q_mult + (active ? l0 + lane : l0);      // idle lanes copy the chunk's first query
+#endif
     const float qx = __ldg(queries + qi * 3), qy = __ldg(queries + qi * 3 + 1), qz = __ldg(queries + qi * 3 + 2);
     const size_t cell_base = (size_t)b * G * G * G;
     const GridParams g = grid_params(bbox_ord, b, G);
@@ -724,8 +740,12 @@ static int nearest_neighbor_impl(const float* queries, const float* points, int3
     if (rc) return rc;
     if (q_counts && q_mult > 0 && !nn_use_thread_walk() && !nn_use_brick_for_groups()) {
         // grouped queries: no query binning, one warp per (chunk of a) group in the original order
+#if NN_DENSE
+        const long long warps = ((long long)Q + 31) / 32;
+#else
         const int cpg = (q_mult + 31) / 32;
         const long long warps = (long long)(Q / q_mult) * cpg;
+#endif
         dim3 grid(cdiv(warps, 4), B);
         prof_begin(PROF_NN_QUERY, st);
         nn_query_group_kernel<<<grid, 128, 0, st>>>(queries, Q, q_counts, q_mult, G, pg.bbox_ord, pg.cell_start, pg.cell_end, pg.sorted, pg.mask, result);
