@@ -5,7 +5,8 @@ config 4  res 100, GLOBAL batch 4, "adjacency rebuild + vertex collapse every st
           vertex adjacency A10, tet-tet sharing A12, face-face adjacency A13 -- collapses the (4T,3) tet-soup vertices A14, and runs the
           full loss forward+backward on the rebuilt topology.  Strong scaling of the 4 samples: N <= 4 ranks take 4/N samples each;
           at N = 8 ranks 2k and 2k+1 SHARE sample k: each takes half of its query points, half of its GT points and half of the
-          surface samples per boundary face, with loss weight 1/2 (so the all-reduced gradient is the same sum); the topology rebuild
+          surface samples per boundary face, with loss weight 1/2 (energies, normal and surface-distance terms add up to exactly the
+          unsplit loss; the chamfer and the masked occupancy means become the average of two half-sample estimates); the topology rebuild
           and the per-tet energies are replicated work on every rank (recompute instead of broadcasting).
 config 5  diff_render: res-40 grid x tetcoef 2.5, 64 cameras on a radius-4 sphere, 800x800, ALL pixels, K = 300; the 64 views are
           sharded over the ranks, each rank renders + back-propagates its views, ONE all-reduce of [d pointmov (V,3), d features
