@@ -166,11 +166,12 @@ __global__ void __launch_bounds__(256) face_stats_kernel(const float* __restrict
             r = fmaxf(r, sqrtf(dx * dx + dy * dy + dz * dz));
         }
         if (pre) {                                   // query-independent half of the distance, once per face
-            FacePre fp;
+            __align__(16) float fp_buf[FACEPRE_FLOATS];          // 16-byte aligned: copied out below as eight float4
+            FacePre& fp = *reinterpret_cast<FacePre*>(fp_buf);
             face_precompute(t, fp);
             // this face's own bounding radius around its centroid (inflated like rmax; +inf when undefined: never pruned by it)
             fp.pad[1] = (r == r) ? r * 1.001f + 1e-7f : __int_as_float(0x7f800000);
-            const float4* src = reinterpret_cast<const float4*>(&fp);
+            const float4* src = reinterpret_cast<const float4*>(fp_buf);
             float4* dst = pre + ((size_t)b * Fmax + f) * 8;
 #pragma unroll
             for (int m = 0; m < 8; ++m) dst[m] = src[m];
