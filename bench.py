@@ -128,7 +128,10 @@ def _reference_deftet_class():
     arc = os.path.join(ROOT, "oracle", "_ref", "reference_py.zip")
     if not os.path.exists(arc):
         return None
+    import atexit
+    import shutil
     d = tempfile.mkdtemp(prefix="deftet_ref_py_")
+    atexit.register(shutil.rmtree, d, True)
     with zipfile.ZipFile(arc) as z:
         z.extractall(d)
     saved = {k: sys.modules.get(k) for k in ("kaolin", "utils", "utils.tet_utils", "utils.mesh_utils", "layers", "layers.DefTet",
