@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) pg_bbox_kernel(const float* __restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(256) pg_count_kernel(const float* __restrict__ items, bool tri, int N, int G, bool brick,
+__global__ void __launch_bounds__(256) pg_count_kernel(const float* __restrict__ items, bool tri, int N, int G, int xmult, bool brick,
                                                        const int32_t* __restrict__ counts, const unsigned* __restrict__ bbox_ord, unsigned* __restrict__ cell_count,
                                                        unsigned* __restrict__ cell_of) {
     int b = blockIdx.y;
@@ -53,8 +53,14 @@ __global__ void __launch_bounds__(256) pg_count_kernel(const float* __restrict__
     GridParams g = grid_params(bbox_ord, b, G);
     float x, y, z;
     load_item(items, (size_t)b * N + i, tri, x, y, z);
-    int cx = cell_coord(x, g.ox, g.inv_h, G), cy = cell_coord(y, g.oy, g.inv_h, G), cz = cell_coord(z, g.oz, g.inv_h, G);
-    unsigned c = (unsigned)b * G * G * G + cell_index(cx, cy, cz, G, brick);
+    int cy = cell_coord(y, g.oy, g.inv_h, G), cz = cell_coord(z, g.oz, g.inv_h, G);
+    unsigned c;
+    if (xmult > 1) {          // row-major, x refined: (z, y) rows of G * xmult cells
+        const int Gx = G * xmult;
+        c = ((unsigned)b * G * G + (unsigned)cz * G + cy) * Gx + cell_coord(x, g.ox, g.inv_h * (float)xmult, Gx);
+    } else {
+        c = (unsigned)b * G * G * G + cell_index(cell_coord(x, g.ox, g.inv_h, G), cy, cz, G, brick);
+    }
     cell_of[(size_t)b * N + i] = c;
     atomicAdd(&cell_count[c], 1u);
 }
@@ -90,16 +96,17 @@ __global__ void pg_brick_mask_kernel(const unsigned* __restrict__ cell_start, co
     mask[w] = m;
 }
 
-size_t pointgrid_workspace_bytes(int B, int N, int G, bool with_mask, bool brick) {
+size_t pointgrid_workspace_bytes(int B, int N, int G, bool with_mask, bool brick, int xmult) {
     Workspace ws(nullptr, 0);
     PointGrid pg;
-    pointgrid_carve(pg, B, N, G, with_mask, brick, ws);
+    pointgrid_carve(pg, B, N, G, with_mask, brick, ws, xmult);
     return ws.off;
 }
 
-bool pointgrid_carve(PointGrid& pg, int B, int N, int G, bool with_mask, bool brick, Workspace& ws) {
+bool pointgrid_carve(PointGrid& pg, int B, int N, int G, bool with_mask, bool brick, Workspace& ws, int xmult) {
     pg.B = B; pg.N = N; pg.G = G; pg.brick = brick;
-    size_t cells = (size_t)B * G * G * G;
+    pg.xmult = (brick || xmult < 1) ? 1 : xmult;
+    size_t cells = (size_t)B * G * G * G * pg.xmult;
     // bbox_ord and cell_start are adjacent (bbox padded to 256 B) so that one memset clears both
     pg.bbox_ord = ws.take<unsigned>((size_t)B * 6);
     pg.cell_start = ws.take<unsigned>(cells);
@@ -117,7 +124,7 @@ int pointgrid_build(PointGrid& pg, const float* items, bool tri, cudaStream_t st
 
 int pointgrid_build_ragged(PointGrid& pg, const float* items, bool tri, const int32_t* counts, cudaStream_t st) {
     const int B = pg.B, N = pg.N, G = pg.G;
-    size_t cells = (size_t)B * G * G * G;
+    size_t cells = (size_t)B * G * G * G * pg.xmult;
     if (cells >= (1ull << 31) || (size_t)B * N >= (1ull << 31)) { set_error("pointgrid: problem too large for 32-bit cell ids"); return DTB_EOVERFLOW; }
     DTB_CUDA(cudaMemsetAsync(pg.bbox_ord, 0, pg.clear_bytes, st));
     if (N > 0) {
@@ -127,7 +134,7 @@ int pointgrid_build_ragged(PointGrid& pg, const float* items, bool tri, const in
     }
     if (N > 0) {
         dim3 gc(cdiv(N, 256), B);
-        pg_count_kernel<<<gc, 256, 0, st>>>(items, tri, N, G, pg.brick, counts, pg.bbox_ord, pg.cell_start, pg.cell_of);
+        pg_count_kernel<<<gc, 256, 0, st>>>(items, tri, N, G, pg.xmult, pg.brick, counts, pg.bbox_ord, pg.cell_start, pg.cell_of);
         DTB_LAUNCH_CHECK("pg_count");
     }
     int rc = exclusive_scan_u32_dup(pg.cell_start, pg.cell_start, pg.cell_end, cells, nullptr, pg.scan_ws, pg.scan_ws_bytes, st);

@@ -21,6 +21,7 @@ struct GridParams {     // per-sample, computed on device from bbox_ord
 
 struct PointGrid {
     int B, N, G;
+    int xmult;                // row-major layout only: cells along x are xmult times finer (G * xmult per row); 1 = cubic cells
     bool brick;               // cell order: false = row-major (z,y,x); true = 4x4x4 bricks (G % 4 == 0), 64 cells per brick
     unsigned* bbox_ord;       // [B][6]
     unsigned* cell_start;     // [B*G^3]
@@ -59,9 +60,9 @@ __device__ __forceinline__ int cell_coord(float x, float o, float inv_h, int G) 
     return (int)f;
 }
 
-size_t pointgrid_workspace_bytes(int B, int N, int G, bool with_mask, bool brick);
+size_t pointgrid_workspace_bytes(int B, int N, int G, bool with_mask, bool brick, int xmult = 1);
 // carve a PointGrid out of ws (returns false if it does not fit)
-bool pointgrid_carve(PointGrid& pg, int B, int N, int G, bool with_mask, bool brick, Workspace& ws);
+bool pointgrid_carve(PointGrid& pg, int B, int N, int G, bool with_mask, bool brick, Workspace& ws, int xmult = 1);
 // enqueue: bbox -> count -> scan -> fill (-> mask).  items: (B,N,3) f32 contiguous, or, when
 // `tri_centroid` is true, (B,N,3,3) triangles binned by centroid.
 int pointgrid_build(PointGrid& pg, const float* items, bool tri_centroid, cudaStream_t st);

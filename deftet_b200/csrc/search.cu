@@ -69,6 +69,9 @@ struct PitSoup {
 #ifndef PIT_UNROLL
 #define PIT_UNROLL 1
 #endif
+#ifndef PIT_XMULT
+#define PIT_XMULT 4            // x refinement of the query-point grid rows
+#endif
 #ifndef PIT_MIN_CTAS
 #define PIT_MIN_CTAS 1
 #endif
@@ -112,14 +115,17 @@ __global__ void __launch_bounds__(128, PIT_MIN_CTAS) pit_tet_kernel(Src src, int
     if (mx[0] < g.ox || mx[1] < g.oy || mx[2] < g.oz || mn[0] > g.ox + gmax * 1.0001f || mn[1] > g.oy + gmax * 1.0001f ||
         mn[2] > g.oz + gmax * 1.0001f)
         return;
-    int x0 = cell_coord(mn[0], g.ox, g.inv_h, G), x1 = cell_coord(mx[0], g.ox, g.inv_h, G);
+    // rows are (z, y) lines of G * PIT_XMULT cells: the finer x resolution only tightens the [x0, x1] candidate range of a row (still
+    // two look-ups per row), it adds no rows
+    const int Gx = G * PIT_XMULT;
+    int x0 = cell_coord(mn[0], g.ox, g.inv_h * (float)PIT_XMULT, Gx), x1 = cell_coord(mx[0], g.ox, g.inv_h * (float)PIT_XMULT, Gx);
     int y0 = cell_coord(mn[1], g.oy, g.inv_h, G), y1 = cell_coord(mx[1], g.oy, g.inv_h, G);
     int z0 = cell_coord(mn[2], g.oz, g.inv_h, G), z1 = cell_coord(mx[2], g.oz, g.inv_h, G);
     int* hb = hit + (size_t)b * P;
-    const size_t cbase = (size_t)b * G * G * G;
+    const size_t cbase = (size_t)b * G * G * Gx;
     for (int z = z0; z <= z1; ++z)
         for (int y = y0; y <= y1; ++y) {
-            size_t row = cbase + ((size_t)z * G + y) * G;
+            size_t row = cbase + ((size_t)z * G + y) * Gx;
             unsigned j0 = cell_start[row + x0], j1 = cell_end[row + x1];
 #if PIT_UNROLL > 1
             for (unsigned j = j0; j < j1; j += PIT_UNROLL) {              // loads first: PIT_UNROLL candidates in flight per lane
@@ -614,7 +620,7 @@ extern "C" int dtb_point_in_tet_grid_res(int T, int P) {
 }
 extern "C" size_t dtb_point_in_tet_workspace(int B, int P, int T, int G) {
     if (G <= 0) G = dtb_point_in_tet_grid_res(T, P);
-    return pointgrid_workspace_bytes(B, P, G, false, false) + align_up((size_t)B * P * sizeof(int), 256) +
+    return pointgrid_workspace_bytes(B, P, G, false, false, PIT_XMULT) + align_up((size_t)B * P * sizeof(int), 256) +
            align_up((size_t)B * T * sizeof(int), 256) + align_up((size_t)B * sizeof(int), 256);
 }
 
@@ -626,7 +632,7 @@ static int point_in_tet_impl(Src src, const float* points, int B, int T, int P, 
     if (G <= 0) G = dtb_point_in_tet_grid_res(T, P);
     Workspace ws(workspace, workspace_bytes);
     PointGrid pg;
-    pointgrid_carve(pg, B, P, G, false, false, ws);
+    pointgrid_carve(pg, B, P, G, false, false, ws, PIT_XMULT);
     int* hit = ws.take<int>((size_t)B * P);
     int* weak_list = ws.take<int>((size_t)B * T);
     int* n_weak = ws.take<int>(B);
