@@ -11,38 +11,97 @@
 namespace dtb {
 
 // ---- A9 -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bf_flag_kernel(const int32_t* __restrict__ face_tet, const float* __restrict__ occ, int T, int F,
-                                                      unsigned* __restrict__ flag) {
-    int b = blockIdx.y;
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
-    int2 t = reinterpret_cast<const int2*>(face_tet)[f];
-    float s = occ[(size_t)b * T + t.x] + occ[(size_t)b * T + t.y];     // tet_face_occ_bxf (deftet.py:189)
-    flag[(size_t)b * F + f] = (s == 1.0f) ? 1u : 0u;
-}
+// Single pass: a tile of BF_TILE faces per CTA (ticketed per sample, so a tile only ever waits for tiles that already run);
+// every thread flags its BF_ITEMS consecutive faces (occupancy of the two tets sums to exactly 1, deftet.py:189), the CTA scans the
+// flags, warp 0 publishes the tile's count and sums its predecessors' (chained look-back, 32 tiles per step, the scheme of
+// prims.cu's scan), and the flagged faces are written straight to their slots in face-id order -- no flag array, no separate scan
+// (round 1: three launches and ~80 MB of traffic for 18 MB of algorithmic bytes).
+constexpr int BF_THREADS = 256;
+constexpr int BF_ITEMS = 4;
+constexpr int BF_TILE = BF_THREADS * BF_ITEMS;
 
-__global__ void __launch_bounds__(256) bf_compact_kernel(const int32_t* __restrict__ face, const int32_t* __restrict__ face_tet,
-                                                         const float* __restrict__ occ, int T, int F, int Fmax,
-                                                         const unsigned* __restrict__ pos, const unsigned* __restrict__ flag,
-                                                         int32_t* __restrict__ out, int32_t* __restrict__ counts, int* __restrict__ overflow) {
-    int b = blockIdx.y;
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
-    size_t i = (size_t)b * F + f;
-    unsigned base = pos[(size_t)b * F];
-    if (f == F - 1) {
-        unsigned n = pos[i] + flag[i] - base;
-        if (n > (unsigned)Fmax) { atomicExch(overflow, 1); n = Fmax; }
+__global__ void __launch_bounds__(BF_THREADS) bf_fused_kernel(const int32_t* __restrict__ face, const int32_t* __restrict__ face_tet,
+                                                              const float* __restrict__ occ, int T, int F, int Fmax, int n_tiles,
+                                                              unsigned long long* state, unsigned* ticket, int32_t* __restrict__ out,
+                                                              int32_t* __restrict__ counts, int* __restrict__ overflow) {
+    __shared__ unsigned s_warp[BF_THREADS / 32];
+    __shared__ unsigned s_tile, s_prefix, s_total;
+    const int b = blockIdx.y;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket + b, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* ob = occ + (size_t)b * T;
+    const int f0 = (int)tile * BF_TILE + threadIdx.x * BF_ITEMS;
+    unsigned bits = 0, flips = 0;
+#pragma unroll
+    for (int k = 0; k < BF_ITEMS; ++k) {
+        const int f = f0 + k;
+        if (f < F) {
+            const int2 t = reinterpret_cast<const int2*>(face_tet)[f];
+            const float o0 = ob[t.x], o1 = ob[t.y];
+            if (o0 + o1 == 1.0f) bits |= 1u << k;                         // tet_face_occ_bxf (deftet.py:189)
+            if (o0 == 1.0f) flips |= 1u << k;                             // change_idx: tet-0 side occupied -> reversed winding (:191-194)
+        }
+    }
+    const unsigned cnt = __popc(bits);
+    unsigned incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = lane < BF_THREADS / 32 ? s_warp[lane] : 0u, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += y; }
+        if (lane < BF_THREADS / 32) s_warp[lane] = wi - w;                // exclusive prefix of the warp totals
+        const unsigned btot = __shfl_sync(0xffffffffu, wi, 31);
+        volatile unsigned long long* st = state + (size_t)b * n_tiles;
+        unsigned prefix = 0;
+        if (tile == 0) {
+            if (lane == 0) st[0] = (2ull << 32) | btot;
+        } else {
+            if (lane == 0) st[tile] = (1ull << 32) | btot;
+            __threadfence();
+            int hi = (int)tile - 1;
+            for (;;) {
+                const int p = hi - lane;
+                const unsigned long long wv = (p >= 0) ? st[p] : (2ull << 32);
+                const unsigned fl = (unsigned)(wv >> 32);
+                const unsigned ready = __ballot_sync(0xffffffffu, fl != 0u), inc = __ballot_sync(0xffffffffu, fl == 2u);
+                const int first = inc ? (__ffs(inc) - 1) : 32;
+                const unsigned need = (first >= 32) ? 0xffffffffu : ((2u << first) - 1u);
+                if ((ready & need) != need) continue;
+                unsigned val = (lane <= first) ? (unsigned)wv : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                prefix += val;
+                if (first < 32) break;
+                hi -= 32;
+            }
+            if (lane == 0) st[tile] = (2ull << 32) | (prefix + btot);
+        }
+        __threadfence();
+        if (lane == 0) { s_prefix = prefix; s_total = prefix + btot; }
+    }
+    __syncthreads();
+    unsigned slot = s_prefix + s_warp[warp] + (incl - cnt);
+    if ((int)(tile + 1) * BF_TILE >= F && threadIdx.x == 0) {             // the sample's last tile knows the count
+        unsigned n = s_total;
+        if (n > (unsigned)Fmax) { atomicExch(overflow, 1); n = (unsigned)Fmax; }
         counts[b] = (int)n;
     }
-    if (!flag[i]) return;
-    unsigned k = pos[i] - base;
-    if (k >= (unsigned)Fmax) return;
-    int a = face[f * 3], bb = face[f * 3 + 1], c = face[f * 3 + 2];
-    int t0 = face_tet[f * 2];
-    bool flip = occ[(size_t)b * T + t0] == 1.0f;       // change_idx: tet-0 side occupied -> reversed winding (deftet.py:191-194)
-    int32_t* o = out + ((size_t)b * Fmax + k) * 3;
-    o[0] = flip ? c : a; o[1] = bb; o[2] = flip ? a : c;
+#pragma unroll
+    for (int k = 0; k < BF_ITEMS; ++k) {
+        if (!(bits & (1u << k))) continue;
+        const unsigned dst = slot++;
+        if (dst >= (unsigned)Fmax) continue;
+        const int f = f0 + k;
+        const int a = face[f * 3], bb = face[f * 3 + 1], c = face[f * 3 + 2];
+        const bool flip = (flips >> k) & 1u;
+        int32_t* o = out + ((size_t)b * Fmax + dst) * 3;
+        o[0] = flip ? c : a; o[1] = bb; o[2] = flip ? a : c;
+    }
 }
 
 // ---- A3: sample points on the predicted surface ------------------------------------------------------
@@ -140,8 +199,8 @@ __global__ void __launch_bounds__(256) face_soup_kernel(const float* __restrict_
 using namespace dtb;
 
 extern "C" size_t dtb_boundary_faces_workspace(int B, int F) {
-    size_t n = (size_t)B * F;
-    return align_up(n * 4, 256) * 2 + scan_workspace_bytes(n) + 512;
+    size_t tiles = ((size_t)(F > 0 ? F : 1) + BF_TILE - 1) / BF_TILE;
+    return align_up((size_t)B * tiles * sizeof(unsigned long long) + (size_t)B * sizeof(unsigned), 256) + 512;
 }
 
 extern "C" int dtb_boundary_faces(const int32_t* face_fx3, const int32_t* face_tet_fx2, const float* occ, int B, int T, int F, int Fmax,
@@ -151,20 +210,16 @@ extern "C" int dtb_boundary_faces(const int32_t* face_fx3, const int32_t* face_t
     DTB_REQUIRE(B > 0 && F >= 0 && Fmax >= 0, "boundary_faces: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
     if (F == 0) { DTB_CUDA(cudaMemsetAsync(out_counts, 0, B * sizeof(int), st)); return DTB_OK; }
-    size_t n = (size_t)B * F;
+    const int tiles = cdiv(F, BF_TILE);
     Workspace ws(workspace, workspace_bytes);
-    unsigned* flag = ws.take<unsigned>(n);
-    unsigned* pos = ws.take<unsigned>(n);
-    size_t sb = scan_workspace_bytes(n);
-    void* sws = ws.take<char>(sb);
+    const size_t state_bytes = (size_t)B * tiles * sizeof(unsigned long long) + (size_t)B * sizeof(unsigned);
+    unsigned long long* state = (unsigned long long*)ws.take<char>(state_bytes);
     if (!ws.ok || !workspace) { set_error("boundary_faces: workspace too small (%zu < %zu)", workspace_bytes, ws.off); return DTB_EWORKSPACE; }
-    dim3 grid(cdiv(F, 256), B);
-    bf_flag_kernel<<<grid, 256, 0, st>>>(face_tet_fx2, occ, T, F, flag);
-    DTB_LAUNCH_CHECK("bf_flag");
-    int rc = exclusive_scan_u32(flag, pos, n, nullptr, sws, sb, st);
-    if (rc) return rc;
-    bf_compact_kernel<<<grid, 256, 0, st>>>(face_fx3, face_tet_fx2, occ, T, F, Fmax, pos, flag, out_faces, out_counts, overflow);
-    DTB_LAUNCH_CHECK("bf_compact");
+    unsigned* ticket = (unsigned*)(state + (size_t)B * tiles);
+    DTB_CUDA(cudaMemsetAsync(state, 0, state_bytes, st));
+    dim3 grid(tiles, B);
+    bf_fused_kernel<<<grid, BF_THREADS, 0, st>>>(face_fx3, face_tet_fx2, occ, T, F, Fmax, tiles, state, ticket, out_faces, out_counts, overflow);
+    DTB_LAUNCH_CHECK("bf_fused");
     return DTB_OK;
 }
 
