@@ -17,7 +17,10 @@ namespace dtb {
 // prims.cu's scan), and the flagged faces are written straight to their slots in face-id order -- no flag array, no separate scan
 // (round 1: three launches and ~80 MB of traffic for 18 MB of algorithmic bytes).
 constexpr int BF_THREADS = 256;
-constexpr int BF_ITEMS = 4;
+#ifndef BF_ITEMS_N
+#define BF_ITEMS_N 4
+#endif
+constexpr int BF_ITEMS = BF_ITEMS_N;
 constexpr int BF_TILE = BF_THREADS * BF_ITEMS;
 
 __global__ void __launch_bounds__(BF_THREADS) bf_fused_kernel(const int32_t* __restrict__ face, const int32_t* __restrict__ face_tet,
